@@ -1,0 +1,138 @@
+"""Import the UNMODIFIED reference (``/root/reference``) under the alias package
+``skyeye_ref`` and apply the enumerated repairs R1-R4 + (inj) of SURVEY.md §0.2.
+
+Only usable in the build container (the GPU box has no ``/root/reference``).
+Used by ``tests/golden/make_golden.py`` to generate the committed fixtures and
+by the ``reference``-marked CPU tests that pin the oracle to the reference.
+Nothing here copies reference source: modules are imported from where they lie.
+"""
+from __future__ import annotations
+
+import importlib
+import math
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("SKYEYE_REFERENCE_ROOT", "/root/reference")
+ALIAS = "skyeye_ref"
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, "skyeye", "core", "models", "detector.py"))
+
+
+def _pkg(name: str, path: str) -> types.ModuleType:
+    m = sys.modules.get(name)
+    if m is None:
+        m = types.ModuleType(name)
+        m.__path__ = [path]  # namespace-like: submodules resolve by path, __init__ is NOT executed
+        m.__package__ = name
+        sys.modules[name] = m
+    return m
+
+
+def load():
+    """Returns a namespace with the reference modules (detector, backbone, blocks,
+    attention, metrics) and the repaired classes."""
+    if not available():
+        raise RuntimeError(f"reference not found under {REF_ROOT}")
+    base = os.path.join(REF_ROOT, "skyeye")
+    _pkg(ALIAS, base)
+    _pkg(ALIAS + ".core", os.path.join(base, "core"))
+    _pkg(ALIAS + ".core.models", os.path.join(base, "core", "models"))
+    _pkg(ALIAS + ".utils", os.path.join(base, "utils"))  # bypasses the broken utils/__init__ (X9)
+    # (inj) stub plotting deps that are absent here (X9)
+    for stub in ("matplotlib", "matplotlib.pyplot", "seaborn"):
+        if stub not in sys.modules:
+            try:
+                importlib.import_module(stub)
+            except Exception:
+                sys.modules[stub] = types.ModuleType(stub)
+    import torch
+    import torch.nn as nn
+    import torchvision
+
+    blocks = importlib.import_module(ALIAS + ".core.models.blocks")
+    attention = importlib.import_module(ALIAS + ".core.models.attention")
+    backbone = importlib.import_module(ALIAS + ".core.models.backbone")
+    detector = importlib.import_module(ALIAS + ".core.models.detector")
+    metrics = importlib.import_module(ALIAS + ".utils.metrics")
+    metrics.torchvision = torchvision  # (inj) X7: module never imports torchvision
+
+    # R1 (X1): guard the bias-less nn.Linear in _initialize_weights (detector.py:326-341)
+    def _initialize_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+                m.weight.data.normal_(0, math.sqrt(2.0 / n))
+                if m.bias is not None:
+                    m.bias.data.zero_()
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+            elif isinstance(m, nn.Linear):
+                m.weight.data.normal_(0, 0.01)
+                if m.bias is not None:
+                    m.bias.data.zero_()
+
+    detector.SkyEyeDetector._initialize_weights = _initialize_weights
+
+    # R2 (X2): report the true channel counts of [s2, s3, s4] (backbone.py:139-143 vs :38-42,99)
+    _orig_bb_init = backbone.SkyEyeBackbone.__init__
+
+    def _bb_init(self, base_channels=64, depth_multiple=1.0, width_multiple=1.0):
+        _orig_bb_init(self, base_channels, depth_multiple, width_multiple)
+        self.channels = [max(round(base_channels * k * width_multiple), 1) for k in (4, 8, 16)]
+
+    if not getattr(backbone.SkyEyeBackbone, "_r2", False):
+        backbone.SkyEyeBackbone.__init__ = _bb_init
+        backbone.SkyEyeBackbone._r2 = True
+
+    # R4 (X4): K is projected to the query width so q*k type-checks (attention.py:168,201,222-229)
+    class CrossLayerAttentionR4(attention.CrossLayerAttention):
+        def __init__(self, query_channels, key_channels, **kw):
+            super().__init__(query_channels, key_channels, **kw)
+            self.key_projection = nn.Conv2d(key_channels, query_channels, kernel_size=1)
+            self.key_channels = query_channels  # only consumed by k.view at attention.py:222
+
+    # D3 + D4: EnhancedSkyEyeDetector with R4 CLA and TransformerLayer heads
+    class SkyEyeL(detector.SkyEyeDetector):
+        def __init__(self, cfg):
+            super().__init__(cfg)
+            c3, c4, c5 = self.neck.out_channels
+            self.cross_attention_p5_p4 = CrossLayerAttentionR4(c4, c5, region_size=2, heads=4)
+            self.cross_attention_p4_p3 = CrossLayerAttentionR4(c3, c4, region_size=2, heads=4)
+            hd = cfg.get("head_dim", 64)
+            self.head_transformers = nn.ModuleList(
+                attention.TransformerLayer(dim=c, num_heads=max(c // hd, 1)) for c in (c3, c4, c5))
+
+        def forward(self, x):  # detector.py:471-501 + D4
+            feats, _ = self.backbone(x)
+            p3, p4, p5 = self.neck(feats)
+            p4e = self.cross_attention_p5_p4(p4, p5) + p4
+            p3e = self.cross_attention_p4_p3(p3, p4e) + p3
+            lv = [t(f) for t, f in zip(self.head_transformers, (p3e, p4e, p5))]
+            outs = self.detection_head(lv)
+            det = self.detection_head.process_detections(outs, x.shape[2:])
+            return det, outs
+
+    ns = types.SimpleNamespace(blocks=blocks, attention=attention, backbone=backbone,
+                               detector=detector, metrics=metrics,
+                               CrossLayerAttentionR4=CrossLayerAttentionR4, SkyEyeL=SkyEyeL,
+                               torch=torch)
+    return ns
+
+
+def build_reference_model(cfg: dict):
+    """Reference detector (+repairs) for an oracle config dict (see oracle.model.VARIANTS)."""
+    ns = load()
+    rcfg = {"nc": cfg["nc"], "depth_multiple": cfg["depth_multiple"], "width_multiple": 1.0,
+            "base_channels": cfg["base_channels"], "head_dim": cfg.get("head_dim", 64)}
+    if cfg.get("anchors") is not None:
+        rcfg["anchors"] = cfg["anchors"]
+    if cfg.get("enhanced"):
+        m = ns.SkyEyeL(rcfg)
+    else:
+        m = ns.detector.SkyEyeDetector(rcfg)
+    return m.eval()
