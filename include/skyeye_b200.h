@@ -1,0 +1,131 @@
+/* skyeye_b200.h -- C ABI of libskyeye_b200.so: the B200 (sm_100a) kernels under SkyEye's batched
+ * detector forward path (backbone -> neck -> CLA -> transformer heads -> decode -> NMS).
+ *
+ * The reference (pure Python/PyTorch) has no FFI; its seam for this path is nn.Module.forward on
+ * torch tensors plus the free function non_max_suppression.  Each entry point below names the
+ * reference code it replaces (file:line under /root/reference).  The Python host package
+ * (skyeye/...) binds these with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every function returns 0 (SKB_OK) or a negative error code; skb_last_error() has the message
+ *     (thread-local).  No CPU fallback: on a non-sm_100 device compute calls return SKB_ERR_ARCH.
+ *   - the library never allocates or frees device memory: inputs, outputs and workspaces are
+ *     caller-owned (the Python host allocates them with torch.empty and passes data_ptr()).
+ *   - every launch goes to the explicit `stream` (a cudaStream_t passed as void*); no internal
+ *     synchronisation, no host-visible results => CUDA-graph capturable.
+ *   - activations are NHWC; a view addresses a channel slice of a wider buffer (concat fusion).
+ */
+#ifndef SKYEYE_B200_H_
+#define SKYEYE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKB_VERSION 100 /* 0.1.0 */
+
+#define SKB_OK 0
+#define SKB_ERR_ARG (-1)         /* bad shape / alignment / null pointer */
+#define SKB_ERR_ARCH (-2)        /* device is not sm_100 */
+#define SKB_ERR_CUDA (-3)        /* CUDA runtime / driver error */
+#define SKB_ERR_UNSUPPORTED (-4) /* valid request the kernels do not cover (message says why) */
+#define SKB_ERR_WORKSPACE (-5)   /* workspace too small (see skb_*_workspace_bytes) */
+
+#define SKB_BF16 0
+#define SKB_F32 1
+
+#define SKB_ACT_NONE 0
+#define SKB_ACT_SILU 1 /* ConvolutionBlock, blocks.py:34 */
+#define SKB_ACT_RELU 2 /* TransformerLayer FFN, attention.py:274 */
+
+/* NHWC view: element (n,y,x,ch) lives at ptr + ((n*h + y)*w + x)*pitch + ch, ch < c <= pitch.
+ * ptr already includes the channel offset of the slice; ptr must be 16-byte aligned. */
+typedef struct skb_view {
+    void* ptr;
+    int32_t n, h, w, c;
+    int32_t pitch; /* elements between consecutive pixels */
+    int32_t dtype; /* SKB_BF16 or SKB_F32 */
+} skb_view;
+
+int skb_version(void);
+const char* skb_last_error(void);
+/* SKB_OK iff the current CUDA device is compute capability 10.x */
+int skb_device_check(void);
+
+/* ---- conv-BN-SiLU implicit GEMM on tcgen05 (TMA im2col tiles, TMEM accumulators) --------------
+ * Replaces ConvolutionBlock.forward (skyeye/core/models/blocks.py:36-38), BottleneckBlock's residual
+ * (blocks.py:88-90), the concat writes of CSPBlock/SPPBlock/FeatureNeck (blocks.py:121-123,149;
+ * detector.py:215,219,224,228), nn.Conv2d 1x1 projections (attention.py:167-170; detector.py:56-59)
+ * and the nn.Linear layers of TransformerLayer (attention.py:265,272-278).
+ *   y = [residual +] act(conv(x, w) + bias)        (fp32 accumulate; bf16 or fp32 store)
+ * x: bf16 view [N,H,W,Cin], Cin % 32 == 0.   w: bf16 [cout_pad][k*k][Cin] (K-major, BN folded),
+ * cout_pad % 32 == 0 (% 64 if > 32), rows >= y->c are zero.   bias: fp32 [cout_pad].
+ * k in {1,3}, stride in {1,2} (pad k/2; stride 2 needs even H, W).  y: view [N,Ho,Wo,Cout] (or
+ * [N,2Ho,2Wo,Cout] when upsample2x != 0: each result is replicated 2x2 = nearest upsampling fused
+ * into the store, detector.py:214,218).  residual (nullable): bf16 view shaped like y, added after
+ * the activation; may alias y (in-place bottleneck update). */
+int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const float* bias, const skb_view* residual,
+                    const skb_view* y, int32_t cout_pad, int32_t ksize, int32_t stride, int32_t act,
+                    int32_t upsample2x, void* stream);
+
+/* ---- layout / pooling / attention-gate kernels (HBM-bound) ------------------------------------ */
+/* FocusBlock space-to-depth (blocks.py:170-181) fused with the NCHW fp32 -> NHWC bf16 conversion:
+ * y[n, y, x, p*3 + c] = img[n, c, 2y + dy(p), 2x + dx(p)], patches TL, BL, TR, BR; channels
+ * 12..y->c-1 are zero-filled.  img: fp32 [N,3,H,W] contiguous. */
+int skb_focus_nchw_f32(const float* img, int32_t n, int32_t h, int32_t w, const skb_view* y, void* stream);
+/* nn.MaxPool2d(5, stride 1, pad 2) (blocks.py:143-144); SPP's 9 and 13 pools are cascades of it. */
+int skb_maxpool5_bf16(const skb_view* x, const skb_view* y, void* stream);
+/* CombinedAttention = ChannelAttention + SpatialAttention (attention.py:37-60, 80-98, 118-130).
+ * w0: fp32 [C/r][C], w1: fp32 [C][C/r], w7: fp32 [2][7][7].  workspace: fp32, see size query. */
+size_t skb_cbam_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t c);
+int skb_cbam_bf16(const skb_view* x, const float* w0, const float* w1, int32_t reduced, const float* w7,
+                  const skb_view* y, void* workspace, size_t workspace_bytes, void* stream);
+/* CrossLayerAttention core in closed form (attention.py:196-238 with R4):
+ * s = scale * sum_{c in head} q * bilinear(k);  a = softmax over image rows;  o = r2 * a * bilinear(v).
+ * q: [N,H,W,Cq]; k: [N,H/2,W/2,Cq]; v: [N,H/2,W/2,Cv]; o: [N,H,W,Cv]; all bf16 views. */
+size_t skb_cla_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t heads);
+int skb_cla_core_bf16(const skb_view* q, const skb_view* k, const skb_view* v, const skb_view* o, int32_t heads,
+                      float scale, float r2, void* workspace, size_t workspace_bytes, void* stream);
+/* nn.LayerNorm over channels (attention.py:268-269, 297, 302), eps 1e-5; x, y bf16 views. */
+int skb_layernorm_bf16(const skb_view* x, const float* gamma, const float* beta, float eps, const skb_view* y,
+                       void* stream);
+/* nn.MultiheadAttention core (attention.py:298): softmax(q k^T * scale) v per (image, head), flash
+ * style on tcgen05 (never materialises N x N).  qkv: bf16 view [B,H,W,3C] = in_proj output (q | k | v
+ * on the channel axis); o: bf16 view [B,H,W,C]; head_dim must be 64. */
+int skb_flash_attn_bf16(const skb_view* qkv, const skb_view* o, int32_t heads, float scale, void* stream);
+
+/* ---- decode (DetectionHead.process_detections, detector.py:88-145) -----------------------------
+ * raw[l]: fp32 view [B,h_l,w_l,>=na*no] (channel = a*no + o, the 1x1 head conv output).
+ * det: fp32 [B, sum_l na*h_l*w_l, no], rows ordered (level, anchor, y, x).
+ * raw_out[l] (nullable): fp32 [B,na,h_l,w_l,no] = the reference's raw_outputs (detector.py:81-82).
+ * anchors: host fp32 [levels][na][2] in pixels (multiplied by stride again, quirk X16). */
+int skb_decode_f32(const skb_view* raw, int32_t levels, int32_t na, int32_t no, const float* anchors_host,
+                   int32_t in_h, int32_t in_w, float* det, float* const* raw_out, void* stream);
+
+/* ---- NMS ---------------------------------------------------------------------------------------
+ * skb_nms_f32: torchvision.ops.nms semantics (call site skyeye/utils/metrics.py:442), bit-exact with
+ * the CPU op: stable descending sort, fp32 IoU with true division and no FMA, suppress iff iou > thr.
+ * boxes [n,4] xyxy, scores [n] (device).  keep: int64 [n] (device), n_keep: int32 (device). */
+size_t skb_nms_workspace_bytes(int32_t n);
+int skb_nms_f32(const float* boxes, const float* scores, int32_t n, float iou_thr, int64_t* keep, int32_t* n_keep,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* skb_nms_batched_f32: the whole reference wrapper non_max_suppression (metrics.py:361-457) for a
+ * batch, no host synchronisation: confidence filter, best-class / multi-label expansion, optional
+ * class filter, top-30000 cap, class-offset boxes, greedy NMS, max_det.
+ * pred: fp32 [B,N,5+nc] (device).  out: fp32 [B,max_det,7] rows [cx,cy,w,h,obj,cls_prob,cls_id]
+ * (compat 0 = reference quirks X8; nc==1 rows use 6 columns) or [x1,y1,x2,y2,conf,cls,0] (compat 1).
+ * out_count: int32 [B].  classes: host int32 [n_classes] or NULL. */
+size_t skb_nms_batched_workspace_bytes(int32_t b, int32_t n, int32_t nc, int32_t multi_label);
+int skb_nms_batched_f32(const float* pred, int32_t b, int32_t n, int32_t nc, float conf_thr, float iou_thr,
+                        const int32_t* classes_host, int32_t n_classes, int32_t agnostic, int32_t multi_label,
+                        int32_t max_det, int32_t compat, float* out, int32_t* out_count, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKYEYE_B200_H_ */

@@ -1,0 +1,411 @@
+// Conv-BN-SiLU as an implicit GEMM on tcgen05 (sm_100a).
+//
+//   D[M = pixels, N = Cout] = sum over (tap, cin-chunk) A_tap[M, 64] * W[N, tap*Cin + chunk]^T
+//
+// * A operand: activations stay NHWC bf16 in HBM.  One M tile is a box of tn x th x tw output pixels
+//   (tn*th*tw <= 128); for every filter tap the TMA engine fetches the correspondingly shifted input
+//   box (5-D tiled tensor map {c, w, parity, h, n}) straight into the canonical K-major SWIZZLE_128B
+//   layout -- im2col never exists in memory and the conv zero padding is TMA out-of-bounds fill.
+//   Stride-2 convs address the input as [N, H/2, 2, W/2, 2*pitch] so a tap selects a (row-parity,
+//   column-parity) plane and the box is dense again.
+// * B operand: weights [Cout_pad][taps*Cin] bf16 (BN folded), 2-D tensor map, same swizzle.
+// * Accumulators: fp32 in TMEM, double buffered (2 x BN columns) so the epilogue of tile i overlaps
+//   the MMAs of tile i+1.  Persistent CTAs, static tile schedule (Cout block fastest).
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue
+//   (tcgen05.ld -> +bias -> SiLU/ReLU -> +residual -> bf16/fp32 store into a channel slice of the
+//   destination buffer; optional 2x2 replication = fused nearest upsample).
+//
+// Replaces ConvolutionBlock.forward (skyeye/core/models/blocks.py:36-38) and friends, see
+// include/skyeye_b200.h.
+#include "common.cuh"
+
+namespace skb {
+
+struct ConvParams {
+    int tiles_w, tiles_h, tiles_n;
+    int tw, th, tn;
+    int n_blocks, total_tiles;
+    int B, Ho, Wo;
+    int k_iters, cchunks;
+    int a_box_bytes;
+    int tap_dw[9], tap_dh[9], tap_ph[9], tap_coff[9];
+    void* out;
+    long long out_pitch;
+    int out_f32, cout, up2;
+    const __nv_bfloat16* res;
+    long long res_pitch;
+    const float* bias;
+    int act;
+};
+
+template <int BN, int BK>
+struct ConvCfg {
+    static constexpr int A_BYTES = 128 * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (196608 / STAGE_BYTES) < 8 ? (196608 / STAGE_BYTES) : 8;
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // 64..512, power of two
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(192, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+    using Cfg = ConvCfg<BN, BK>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr uint32_t SW = BK == 64 ? UMMA_SW128 : UMMA_SW64;
+    constexpr uint32_t SBO = 8 * BK * 2;  // bytes between 8-row groups
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t sA0 = base;
+    const uint32_t sB0 = base + STAGES * Cfg::A_BYTES;
+    const uint32_t bar0 = base + STAGES * Cfg::STAGE_BYTES;
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto tfull = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+    auto tempty = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
+    const uint32_t slot = bar0 + 8u * (2 * STAGES + 4);
+    volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(full(s), 1);
+                mbar_init(empty(s), 1);
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(tfull(s), 1);
+                mbar_init(tempty(s), 4);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(slot, Cfg::TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int nb = tile % p.n_blocks;
+                int mt = tile / p.n_blocks;
+                const int iw = mt % p.tiles_w;
+                mt /= p.tiles_w;
+                const int ih = mt % p.tiles_h;
+                const int in = mt / p.tiles_h;
+                const int w0 = iw * p.tw, h0 = ih * p.th, n0 = in * p.tn;
+                for (int it = 0; it < p.k_iters; ++it) {
+                    const int tap = it / p.cchunks;
+                    const int cc = it - tap * p.cchunks;
+                    mbar_wait(empty(stage), phase ^ 1);
+                    mbar_expect_tx(full(stage), (uint32_t)(p.a_box_bytes + Cfg::B_BYTES));
+                    tma_load_5d(sA0 + stage * Cfg::A_BYTES, &tmA, full(stage), p.tap_coff[tap] + cc * BK,
+                                w0 + p.tap_dw[tap], p.tap_ph[tap], h0 + p.tap_dh[tap], n0);
+                    tma_load_2d(sB0 + stage * Cfg::B_BYTES, &tmB, full(stage), it * BK, nb * BN);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+        int stage = 0, as = 0;
+        uint32_t phase = 0, aphase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            mbar_wait(tempty(as), aphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+            for (int it = 0; it < p.k_iters; ++it) {
+                mbar_wait(full(stage), phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint64_t ad = umma_desc(sA0 + stage * Cfg::A_BYTES, 16, SBO, SW);
+                    const uint64_t bd = umma_desc(sB0 + stage * Cfg::B_BYTES, 16, SBO, SW);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16_ss(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(empty(stage));
+                    if (it == p.k_iters - 1) umma_commit(tfull(as));
+                }
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
+        }
+    } else {
+        // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int hw = p.th * p.tw;
+        const int nl = m / hw;
+        const int rem = m - nl * hw;
+        const int hl = rem / p.tw;
+        const int wl = rem - hl * p.tw;
+        const bool row_in_box = m < p.tn * hw;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int nb = tile % p.n_blocks;
+            int mt = tile / p.n_blocks;
+            const int iw = mt % p.tiles_w;
+            mt /= p.tiles_w;
+            const int ih = mt % p.tiles_h;
+            const int in = mt / p.tiles_h;
+            const int n = in * p.tn + nl, h = ih * p.th + hl, w = iw * p.tw + wl;
+            const bool valid = row_in_box && n < p.B && h < p.Ho && w < p.Wo;
+            const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
+            const size_t opix = p.up2 ? (((size_t)n * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) : pix;
+
+            mbar_wait(tfull(as), aphase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
+                tmem_ld_wait();
+                if (c0 + 32 >= BN) {  // accumulator fully drained into registers: hand TMEM back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty(as));
+                }
+                const int ncol = nb * BN + c0;
+                if (valid) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int col = ncol + g * 8;
+                        if (col < p.cout) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+                            float f[8];
+                            f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
+                            f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+                            f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
+                            f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+                            f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x;
+                            f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+                            f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
+                            f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+                            if (p.act == SKB_ACT_SILU) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+                            } else if (p.act == SKB_ACT_RELU) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
+                            }
+                            if (p.res) {
+                                const uint4 r = *reinterpret_cast<const uint4*>(p.res + pix * p.res_pitch + col);
+                                f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
+                                f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
+                                f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
+                                f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+                            }
+                            if (p.out_f32) {
+                                float* o = reinterpret_cast<float*>(p.out) + opix * p.out_pitch + col;
+                                const float4 o0 = make_float4(f[0], f[1], f[2], f[3]);
+                                const float4 o1 = make_float4(f[4], f[5], f[6], f[7]);
+                                *reinterpret_cast<float4*>(o) = o0;
+                                *reinterpret_cast<float4*>(o + 4) = o1;
+                                if (p.up2) {
+                                    const size_t dx = (size_t)p.out_pitch, dy = (size_t)(2 * p.Wo) * p.out_pitch;
+                                    *reinterpret_cast<float4*>(o + dx) = o0; *reinterpret_cast<float4*>(o + dx + 4) = o1;
+                                    *reinterpret_cast<float4*>(o + dy) = o0; *reinterpret_cast<float4*>(o + dy + 4) = o1;
+                                    *reinterpret_cast<float4*>(o + dy + dx) = o0; *reinterpret_cast<float4*>(o + dy + dx + 4) = o1;
+                                }
+                            } else {
+                                uint4 o4;
+                                o4.x = pack_bf16x2(f[0], f[1]);
+                                o4.y = pack_bf16x2(f[2], f[3]);
+                                o4.z = pack_bf16x2(f[4], f[5]);
+                                o4.w = pack_bf16x2(f[6], f[7]);
+                                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_pitch + col;
+                                *reinterpret_cast<uint4*>(o) = o4;
+                                if (p.up2) {
+                                    const size_t dx = (size_t)p.out_pitch, dy = (size_t)(2 * p.Wo) * p.out_pitch;
+                                    *reinterpret_cast<uint4*>(o + dx) = o4;
+                                    *reinterpret_cast<uint4*>(o + dy) = o4;
+                                    *reinterpret_cast<uint4*>(o + dy + dx) = o4;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <int BN, int BK>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+    using Cfg = ConvCfg<BN, BK>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SKB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    conv_gemm_kernel<BN, BK><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    SKB_LAUNCH_CHECK();
+    return SKB_OK;
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// pick the (tn, th, tw) pixel box with the fewest 128-row MMA tiles; ties -> wider tw (longer runs)
+static void pick_tile(int B, int Ho, int Wo, int& tn, int& th, int& tw, int& tiles) {
+    long best = -1;
+    for (int w = 1; w <= Wo && w <= 128; ++w) {
+        for (int h = 1; h <= Ho && h * w <= 128; ++h) {
+            int n = 128 / (h * w);
+            if (n > B) n = B;
+            if (n < 1) continue;
+            long t = (long)cdiv(Wo, w) * cdiv(Ho, h) * cdiv(B, n);
+            long score = t * 1024 - w;  // fewer tiles first, then wider
+            if (best < 0 || score < best) {
+                best = score;
+                tn = n; th = h; tw = w;
+                tiles = (int)t;
+            }
+        }
+    }
+}
+
+}  // namespace skb
+
+using namespace skb;
+
+extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const float* bias, const skb_view* residual,
+                               const skb_view* y, int32_t cout_pad, int32_t ksize, int32_t stride, int32_t act,
+                               int32_t upsample2x, void* stream) {
+    int rc = check_device();
+    if (rc != SKB_OK) return rc;
+    SKB_REQUIRE(x && y && w_packed && bias && x->ptr && y->ptr, SKB_ERR_ARG, "conv2d: null argument");
+    SKB_REQUIRE(x->dtype == SKB_BF16, SKB_ERR_ARG, "conv2d: input must be bf16");
+    SKB_REQUIRE(ksize == 1 || ksize == 3, SKB_ERR_UNSUPPORTED, "conv2d: kernel size %d (only 1 and 3 are on the path)", ksize);
+    SKB_REQUIRE(stride == 1 || stride == 2, SKB_ERR_UNSUPPORTED, "conv2d: stride %d", stride);
+    const int Cin = x->c;
+    SKB_REQUIRE(Cin % 32 == 0 && Cin >= 32, SKB_ERR_ARG, "conv2d: Cin=%d must be a multiple of 32 (pad the producer)", Cin);
+    SKB_REQUIRE(x->pitch % 8 == 0 && ((uintptr_t)x->ptr & 15) == 0, SKB_ERR_ARG, "conv2d: input view must be 16B aligned (pitch %d)", x->pitch);
+    SKB_REQUIRE(cout_pad % 32 == 0 && (cout_pad == 32 || cout_pad % 64 == 0), SKB_ERR_ARG, "conv2d: cout_pad=%d", cout_pad);
+    SKB_REQUIRE(y->c % 8 == 0 && y->c <= cout_pad, SKB_ERR_ARG, "conv2d: y->c=%d must be a multiple of 8 and <= cout_pad", y->c);
+    SKB_REQUIRE(y->pitch % (y->dtype == SKB_F32 ? 4 : 8) == 0 && ((uintptr_t)y->ptr & 15) == 0, SKB_ERR_ARG, "conv2d: output view alignment");
+    SKB_REQUIRE(((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)bias & 15) == 0, SKB_ERR_ARG, "conv2d: weight/bias alignment");
+    if (stride == 2) SKB_REQUIRE(x->h % 2 == 0 && x->w % 2 == 0, SKB_ERR_UNSUPPORTED, "conv2d: stride 2 needs even H, W (%dx%d)", x->h, x->w);
+    const int Ho = stride == 1 ? x->h : x->h / 2, Wo = stride == 1 ? x->w : x->w / 2;
+    const int up = upsample2x ? 2 : 1;
+    SKB_REQUIRE(y->n == x->n && y->h == Ho * up && y->w == Wo * up, SKB_ERR_ARG, "conv2d: output dims [%d,%d,%d] != expected [%d,%d,%d]",
+                y->n, y->h, y->w, x->n, Ho * up, Wo * up);
+    if (residual) {
+        SKB_REQUIRE(!upsample2x, SKB_ERR_UNSUPPORTED, "conv2d: residual with upsample2x");
+        SKB_REQUIRE(residual->dtype == SKB_BF16 && residual->n == y->n && residual->h == y->h && residual->w == y->w &&
+                        residual->c >= y->c && residual->pitch % 8 == 0 && ((uintptr_t)residual->ptr & 15) == 0,
+                    SKB_ERR_ARG, "conv2d: residual view mismatch");
+    }
+    const int BK = (Cin % 64 == 0) ? 64 : 32;
+    const int taps = ksize * ksize;
+
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    pick_tile(x->n, Ho, Wo, p.tn, p.th, p.tw, p.total_tiles);
+    p.tiles_w = cdiv(Wo, p.tw);
+    p.tiles_h = cdiv(Ho, p.th);
+    p.tiles_n = cdiv(x->n, p.tn);
+    const int m_tiles = p.total_tiles;
+    // output-channel block: minimise waves * per-tile cost (small BN is smem-bandwidth bound)
+    int BN = 32;
+    {
+        double best = 1e30;
+        const int cands[4] = {256, 128, 64, 32};
+        const double pen[4] = {1.0, 1.0, 1.35, 2.0};
+        for (int i = 0; i < 4; ++i) {
+            if (cout_pad % cands[i]) continue;
+            long tiles = (long)m_tiles * (cout_pad / cands[i]);
+            double cost = (double)cdiv((int)tiles, num_sms()) * cands[i] * pen[i];
+            if (cost < best) {
+                best = cost;
+                BN = cands[i];
+            }
+        }
+    }
+    p.n_blocks = cout_pad / BN;
+    p.total_tiles = m_tiles * p.n_blocks;
+    p.B = x->n; p.Ho = Ho; p.Wo = Wo;
+    p.cchunks = Cin / BK;
+    p.k_iters = taps * p.cchunks;
+    p.a_box_bytes = p.tn * p.th * p.tw * BK * 2;
+    const int pad = ksize / 2;
+    for (int r = 0; r < ksize; ++r)
+        for (int s = 0; s < ksize; ++s) {
+            const int t = r * ksize + s;
+            if (stride == 1) {
+                p.tap_dh[t] = r - pad; p.tap_dw[t] = s - pad; p.tap_ph[t] = 0; p.tap_coff[t] = 0;
+            } else if (ksize == 3) {  // input row 2*oh + r - 1 -> (half-res row, parity)
+                p.tap_dh[t] = r == 0 ? -1 : 0; p.tap_ph[t] = r == 1 ? 0 : 1;
+                p.tap_dw[t] = s == 0 ? -1 : 0; p.tap_coff[t] = (s == 1 ? 0 : 1) * x->pitch;
+            } else {  // 1x1 stride 2: input (2*oh, 2*ow)
+                p.tap_dh[t] = 0; p.tap_dw[t] = 0; p.tap_ph[t] = 0; p.tap_coff[t] = 0;
+            }
+        }
+    p.out = y->ptr; p.out_pitch = y->pitch; p.out_f32 = y->dtype == SKB_F32; p.cout = y->c; p.up2 = upsample2x ? 1 : 0;
+    p.res = residual ? (const __nv_bfloat16*)residual->ptr : nullptr;
+    p.res_pitch = residual ? residual->pitch : 0;
+    p.bias = bias; p.act = act;
+
+    CUtensorMap tmA, tmB;
+    {
+        const uint64_t pitchB = (uint64_t)x->pitch * 2;
+        uint64_t dims[5], str[4];
+        uint32_t box[5] = {(uint32_t)BK, (uint32_t)p.tw, 1u, (uint32_t)p.th, (uint32_t)p.tn};
+        if (stride == 1) {
+            dims[0] = Cin; dims[1] = x->w; dims[2] = 1; dims[3] = x->h; dims[4] = x->n;
+            str[0] = pitchB; str[1] = pitchB * x->w; str[2] = pitchB * x->w; str[3] = pitchB * x->w * x->h;
+        } else {
+            dims[0] = (uint64_t)x->pitch + Cin; dims[1] = x->w / 2; dims[2] = 2; dims[3] = x->h / 2; dims[4] = x->n;
+            str[0] = 2 * pitchB; str[1] = pitchB * x->w; str[2] = 2 * pitchB * x->w; str[3] = pitchB * x->w * x->h;
+        }
+        rc = encode_tensor_map(&tmA, x->ptr, 2, 5, dims, str, box, BK * 2);
+        if (rc != SKB_OK) return rc;
+        uint64_t bd[2] = {(uint64_t)taps * Cin, (uint64_t)cout_pad};
+        uint64_t bs[1] = {(uint64_t)taps * Cin * 2};
+        uint32_t bb[2] = {(uint32_t)BK, (uint32_t)BN};
+        rc = encode_tensor_map(&tmB, w_packed, 2, 2, bd, bs, bb, BK * 2);
+        if (rc != SKB_OK) return rc;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+#define SKB_CONV_CASE(bn, bk) \
+    if (BN == bn && BK == bk) return launch_conv<bn, bk>(tmA, tmB, p, st);
+    SKB_CONV_CASE(256, 64) SKB_CONV_CASE(128, 64) SKB_CONV_CASE(64, 64) SKB_CONV_CASE(32, 64)
+    SKB_CONV_CASE(256, 32) SKB_CONV_CASE(128, 32) SKB_CONV_CASE(64, 32) SKB_CONV_CASE(32, 32)
+#undef SKB_CONV_CASE
+    set_error("conv2d: no kernel for BN=%d BK=%d", BN, BK);
+    return SKB_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,499 @@
+// HBM-bound kernels of the forward path: Focus space-to-depth (+NCHW fp32 -> NHWC bf16), 5x5 max
+// pool (SPP cascade), CBAM gate, cross-layer-attention core, LayerNorm.  All are vectorised (16-byte
+// loads/stores of 8 bf16 channels), coalesced along the NHWC channel axis, and write straight into
+// channel slices of concat buffers (views) so torch.cat never materialises.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace skb {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+    f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    return u;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Focus (blocks.py:170-181): y[n, oy, ox, p*3 + c] = img[n, c, 2*oy + dy(p), 2*ox + dx(p)]
+// patches: p0 TL (0,0), p1 BL (1,0), p2 TR (0,1), p3 BR (1,1); channels >= 12 are zero.
+// ---------------------------------------------------------------------------------------------
+__global__ void focus_kernel(const float* __restrict__ img, int N, int H, int W, __nv_bfloat16* __restrict__ y, int pitch, int cpad) {
+    const int Ho = H / 2, Wo = W / 2;
+    const long total = (long)N * Ho * Wo;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % Wo);
+        const int oy = (int)((i / Wo) % Ho);
+        const int n = (int)(i / ((long)Wo * Ho));
+        float v[12];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* base = img + (((long)n * 3 + c) * H + 2 * oy) * W + 2 * ox;
+            const float2 top = *reinterpret_cast<const float2*>(base);
+            const float2 bot = *reinterpret_cast<const float2*>(base + W);
+            v[0 * 3 + c] = top.x;  // TL
+            v[1 * 3 + c] = bot.x;  // BL
+            v[2 * 3 + c] = top.y;  // TR
+            v[3 * 3 + c] = bot.y;  // BR
+        }
+        uint4* o = reinterpret_cast<uint4*>(y + i * pitch);
+        uint4 a, b;
+        a.x = pack_bf16x2(v[0], v[1]); a.y = pack_bf16x2(v[2], v[3]); a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
+        b.x = pack_bf16x2(v[8], v[9]); b.y = pack_bf16x2(v[10], v[11]); b.z = 0u; b.w = 0u;
+        o[0] = a;
+        o[1] = b;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int g = 2; g < cpad / 8; ++g) o[g] = z;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaxPool2d(5, 1, 2) on bf16 NHWC (padding acts as -inf)
+// ---------------------------------------------------------------------------------------------
+__global__ void maxpool5_kernel(const __nv_bfloat16* __restrict__ x, long xpitch, __nv_bfloat16* __restrict__ y, long ypitch,
+                                int N, int H, int W, int C8) {
+    const long total = (long)N * H * W * C8;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % C8);
+        long pix = i / C8;
+        const int px = (int)(pix % W);
+        const int py = (int)((pix / W) % H);
+        const int n = (int)(pix / ((long)W * H));
+        __nv_bfloat162 m[4];
+        const __nv_bfloat162 ninf = __float2bfloat162_rn(-INFINITY);
+        m[0] = m[1] = m[2] = m[3] = ninf;
+        for (int dy = -2; dy <= 2; ++dy) {
+            const int yy = py + dy;
+            if (yy < 0 || yy >= H) continue;
+            for (int dx = -2; dx <= 2; ++dx) {
+                const int xx = px + dx;
+                if (xx < 0 || xx >= W) continue;
+                const uint4 u = *reinterpret_cast<const uint4*>(x + (((long)n * H + yy) * W + xx) * xpitch + g * 8);
+                const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&u);
+                m[0] = __hmax2(m[0], v[0]); m[1] = __hmax2(m[1], v[1]);
+                m[2] = __hmax2(m[2], v[2]); m[3] = __hmax2(m[3], v[3]);
+            }
+        }
+        *reinterpret_cast<uint4*>(y + pix * ypitch + g * 8) = *reinterpret_cast<uint4*>(m);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CBAM (attention.py:37-60, 80-98)
+// ---------------------------------------------------------------------------------------------
+// stage 1: per-image partial channel sums / maxima over a slab of pixels. grid (slabs, N)
+__global__ void cbam_pool_kernel(const __nv_bfloat16* __restrict__ x, long pitch, int HW, int C, int slabs,
+                                 float* __restrict__ psum, float* __restrict__ pmax) {
+    const int n = blockIdx.y, slab = blockIdx.x;
+    const int C8 = C / 8;
+    const int lanes = blockDim.x / C8;  // pixel lanes per channel group (host guarantees >= 1)
+    const int g = threadIdx.x % C8, pl = threadIdx.x / C8;
+    const int per = (HW + slabs - 1) / slabs;
+    const int p0 = slab * per, p1 = min(HW, p0 + per);
+    float s[8], m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; m[j] = -FLT_MAX; }
+    if (pl < lanes) {
+        for (int p = p0 + pl; p < p1; p += lanes) {
+            const uint4 u = *reinterpret_cast<const uint4*>(x + ((long)n * HW + p) * pitch + g * 8);
+            float f[8];
+            unpack8(u, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s[j] += f[j]; m[j] = fmaxf(m[j], f[j]); }
+        }
+    }
+    extern __shared__ float sh[];  // [lanes][C] sums then [lanes][C] maxima
+    float* ss = sh;
+    float* sm = sh + (size_t)lanes * C;
+    if (pl < lanes) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ss[pl * C + g * 8 + j] = s[j]; sm[pl * C + g * 8 + j] = m[j]; }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, b = -FLT_MAX;
+        for (int l = 0; l < lanes; ++l) { a += ss[l * C + c]; b = fmaxf(b, sm[l * C + c]); }
+        psum[((long)n * slabs + slab) * C + c] = a;
+        pmax[((long)n * slabs + slab) * C + c] = b;
+    }
+}
+// stage 2: att[n][c] = sigmoid(W1 relu(W0 avg) + W1 relu(W0 max)). grid N, smem 2C + 2R floats
+__global__ void cbam_mlp_kernel(const float* __restrict__ psum, const float* __restrict__ pmax, int slabs, int HW, int C, int R,
+                                const float* __restrict__ w0, const float* __restrict__ w1, float* __restrict__ att) {
+    extern __shared__ float sh[];
+    float* avg = sh; float* mx = sh + C; float* ha = sh + 2 * C; float* hm = ha + R;
+    const int n = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, b = -FLT_MAX;
+        for (int s = 0; s < slabs; ++s) { a += psum[((long)n * slabs + s) * C + c]; b = fmaxf(b, pmax[((long)n * slabs + s) * C + c]); }
+        avg[c] = a / (float)HW;
+        mx[c] = b;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int r = warp; r < R; r += nw) {
+        float a = 0.f, b = 0.f;
+        for (int c = lane; c < C; c += 32) { const float w = w0[r * C + c]; a += w * avg[c]; b += w * mx[c]; }
+        a = warp_sum(a); b = warp_sum(b);
+        if (lane == 0) { ha[r] = fmaxf(a, 0.f); hm[r] = fmaxf(b, 0.f); }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f;
+        for (int r = 0; r < R; ++r) a += w1[c * R + r] * (ha[r] + hm[r]);
+        att[(long)n * C + c] = 1.0f / (1.0f + expf(-a));
+    }
+}
+// stage 3: per pixel mean/max over channels of x*att. one warp per pixel
+__global__ void cbam_stats_kernel(const __nv_bfloat16* __restrict__ x, long pitch, const float* __restrict__ att, long npix, int HW,
+                                  int C, float* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const long nw = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long p = wid; p < npix; p += nw) {
+        const int n = (int)(p / HW);
+        float s = 0.f, m = -FLT_MAX;
+        for (int c = lane * 8; c < C; c += 256) {
+            const uint4 u = *reinterpret_cast<const uint4*>(x + p * pitch + c);
+            float f[8];
+            unpack8(u, f);
+            const float4 a0 = *reinterpret_cast<const float4*>(att + (long)n * C + c);
+            const float4 a1 = *reinterpret_cast<const float4*>(att + (long)n * C + c + 4);
+            f[0] *= a0.x; f[1] *= a0.y; f[2] *= a0.z; f[3] *= a0.w; f[4] *= a1.x; f[5] *= a1.y; f[6] *= a1.z; f[7] *= a1.w;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s += f[j]; m = fmaxf(m, f[j]); }
+        }
+        s = warp_sum(s);
+        m = warp_max(m);
+        if (lane == 0) { stats[p * 2] = s / (float)C; stats[p * 2 + 1] = m; }
+    }
+}
+// stage 4: sa = sigmoid(conv7x7([mean, max])), y = x * att * sa. one warp per pixel
+__global__ void cbam_apply_kernel(const __nv_bfloat16* __restrict__ x, long xpitch, const float* __restrict__ att,
+                                  const float* __restrict__ stats, const float* __restrict__ w7, int N, int H, int W, int C,
+                                  __nv_bfloat16* __restrict__ y, long ypitch) {
+    __shared__ float sw[98];
+    for (int i = threadIdx.x; i < 98; i += blockDim.x) sw[i] = w7[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long npix = (long)N * H * W;
+    const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const long nw = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long p = wid; p < npix; p += nw) {
+        const int px = (int)(p % W);
+        const int py = (int)((p / W) % H);
+        const int n = (int)(p / ((long)W * H));
+        float acc = 0.f;
+        for (int t = lane; t < 49; t += 32) {
+            const int dy = t / 7 - 3, dx = t % 7 - 3;
+            const int yy = py + dy, xx = px + dx;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                const float2 st = *reinterpret_cast<const float2*>(stats + (((long)n * H + yy) * W + xx) * 2);
+                acc += sw[t] * st.x + sw[49 + t] * st.y;
+            }
+        }
+        acc = warp_sum(acc);
+        const float sa = 1.0f / (1.0f + expf(-acc));
+        for (int c = lane * 8; c < C; c += 256) {
+            const uint4 u = *reinterpret_cast<const uint4*>(x + p * xpitch + c);
+            float f[8];
+            unpack8(u, f);
+            const float4 a0 = *reinterpret_cast<const float4*>(att + (long)n * C + c);
+            const float4 a1 = *reinterpret_cast<const float4*>(att + (long)n * C + c + 4);
+            f[0] = f[0] * a0.x * sa; f[1] = f[1] * a0.y * sa; f[2] = f[2] * a0.z * sa; f[3] = f[3] * a0.w * sa;
+            f[4] = f[4] * a1.x * sa; f[5] = f[5] * a1.y * sa; f[6] = f[6] * a1.z * sa; f[7] = f[7] * a1.w * sa;
+            *reinterpret_cast<uint4*>(y + p * ypitch + c) = pack8(f);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cross-layer attention core (attention.py:196-238 with R4, closed form SURVEY.md §8 A10)
+// ---------------------------------------------------------------------------------------------
+struct Bilin {
+    int y0, y1, x0, x1;
+    float ly, lx;
+};
+// F.interpolate(mode='bilinear', align_corners=False): src = max(0, (dst + .5) * in/out - .5)
+__device__ __forceinline__ Bilin bilin_coords(int y, int x, int H, int W, int Hk, int Wk) {
+    Bilin b;
+    const float sy = fmaxf(((float)y + 0.5f) * ((float)Hk / (float)H) - 0.5f, 0.f);
+    const float sx = fmaxf(((float)x + 0.5f) * ((float)Wk / (float)W) - 0.5f, 0.f);
+    b.y0 = (int)sy; b.x0 = (int)sx;
+    b.y1 = min(b.y0 + 1, Hk - 1); b.x1 = min(b.x0 + 1, Wk - 1);
+    b.ly = sy - (float)b.y0; b.lx = sx - (float)b.x0;
+    return b;
+}
+__device__ __forceinline__ void bilin_load8(const __nv_bfloat16* __restrict__ t, long pitch, int n, int Hk, int Wk, const Bilin& b, int c, float (&o)[8]) {
+    const long base = (long)n * Hk * Wk;
+    float a[8], bb[8], cc[8], d[8];
+    unpack8(*reinterpret_cast<const uint4*>(t + (base + (long)b.y0 * Wk + b.x0) * pitch + c), a);
+    unpack8(*reinterpret_cast<const uint4*>(t + (base + (long)b.y0 * Wk + b.x1) * pitch + c), bb);
+    unpack8(*reinterpret_cast<const uint4*>(t + (base + (long)b.y1 * Wk + b.x0) * pitch + c), cc);
+    unpack8(*reinterpret_cast<const uint4*>(t + (base + (long)b.y1 * Wk + b.x1) * pitch + c), d);
+    const float w00 = (1.f - b.ly) * (1.f - b.lx), w01 = (1.f - b.ly) * b.lx, w10 = b.ly * (1.f - b.lx), w11 = b.ly * b.lx;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = w00 * a[j] + w01 * bb[j] + w10 * cc[j] + w11 * d[j];
+}
+// scores s[n,g,y,x] = scale * sum_{c in head g} q * bilinear(k). one warp per pixel
+__global__ void cla_score_kernel(const __nv_bfloat16* __restrict__ q, long qpitch, const __nv_bfloat16* __restrict__ k, long kpitch,
+                                 int N, int H, int W, int Hk, int Wk, int Cq, int heads, float scale, float* __restrict__ s) {
+    const int lane = threadIdx.x & 31;
+    const long npix = (long)N * H * W;
+    const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const long nw = ((long)gridDim.x * blockDim.x) >> 5;
+    const int cph = Cq / heads;
+    for (long p = wid; p < npix; p += nw) {
+        const int px = (int)(p % W);
+        const int py = (int)((p / W) % H);
+        const int n = (int)(p / ((long)W * H));
+        const Bilin b = bilin_coords(py, px, H, W, Hk, Wk);
+        for (int cbase = 0; cbase < Cq; cbase += 256) {
+            const int c = cbase + lane * 8;
+            float part = 0.f;
+            int head = -1;
+            if (c < Cq) {
+                float qv[8], kv[8];
+                unpack8(*reinterpret_cast<const uint4*>(q + p * qpitch + c), qv);
+                bilin_load8(k, kpitch, n, Hk, Wk, b, c, kv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) part += qv[j] * kv[j];
+                head = c / cph;
+            }
+            // host guarantees 256 % cph == 0: a head never straddles two 256-channel passes
+            const int h_lo = cbase / cph, h_hi = min(heads - 1, (min(Cq, cbase + 256) - 1) / cph);
+            for (int g = h_lo; g <= h_hi; ++g) {
+                const float v = warp_sum(head == g ? part : 0.f);
+                if (lane == 0) s[(((long)n * heads + g) * H + py) * W + px] = v * scale;
+            }
+        }
+    }
+}
+// column softmax statistics over image rows: one thread per (n, g, x)
+__global__ void cla_colstat_kernel(const float* __restrict__ s, int NG, int H, int W, float* __restrict__ st) {
+    const long total = (long)NG * W;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        const long ng = i / W;
+        const float* col = s + ng * H * W + x;
+        float m = -FLT_MAX;
+        for (int y = 0; y < H; ++y) m = fmaxf(m, col[(long)y * W]);
+        float sum = 0.f;
+        for (int y = 0; y < H; ++y) sum += expf(col[(long)y * W] - m);
+        st[i * 2] = m;
+        st[i * 2 + 1] = 1.0f / sum;
+    }
+}
+// o[n,y,x,c] = r2 * softmax_y(s)[head(c)] * bilinear(v)[c]. one warp per pixel
+__global__ void cla_apply_kernel(const float* __restrict__ s, const float* __restrict__ st, const __nv_bfloat16* __restrict__ v, long vpitch,
+                                 int N, int H, int W, int Hk, int Wk, int Cv, int heads, float r2, __nv_bfloat16* __restrict__ o, long opitch) {
+    const int lane = threadIdx.x & 31;
+    const long npix = (long)N * H * W;
+    const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const long nw = ((long)gridDim.x * blockDim.x) >> 5;
+    const int cph = Cv / heads;
+    for (long p = wid; p < npix; p += nw) {
+        const int px = (int)(p % W);
+        const int py = (int)((p / W) % H);
+        const int n = (int)(p / ((long)W * H));
+        const Bilin b = bilin_coords(py, px, H, W, Hk, Wk);
+        float a = 0.f;  // lane g (< heads) holds the attention weight of head g
+        if (lane < heads) {
+            const long ng = (long)n * heads + lane;
+            const float sc = s[(ng * H + py) * W + px];
+            const float2 ms = *reinterpret_cast<const float2*>(st + (ng * W + px) * 2);
+            a = r2 * expf(sc - ms.x) * ms.y;
+        }
+        for (int c = lane * 8; c < Cv; c += 256) {
+            float vv[8];
+            bilin_load8(v, vpitch, n, Hk, Wk, b, c, vv);
+            const float w = __shfl_sync(0xffffffffu, a, c / cph);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vv[j] *= w;
+            *reinterpret_cast<uint4*>(o + p * opitch + c) = pack8(vv);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over channels, one warp per token (C <= 2048, multiple of 8)
+// ---------------------------------------------------------------------------------------------
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long xpitch, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, long ntok, int C, __nv_bfloat16* __restrict__ y, long ypitch) {
+    const int lane = threadIdx.x & 31;
+    const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const long nw = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long t = wid; t < ntok; t += nw) {
+        float f[8][8];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = lane * 8 + i * 256;
+            if (c < C) {
+                unpack8(*reinterpret_cast<const uint4*>(x + t * xpitch + c), f[i]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += f[i][j];
+            }
+        }
+        const float mean = warp_sum(s) / (float)C;
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (lane * 8 + i * 256 < C) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; v += d * d; }
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = lane * 8 + i * 256;
+            if (c < C) {
+                const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+                float o[8];
+                o[0] = (f[i][0] - mean) * rstd * g0.x + b0.x; o[1] = (f[i][1] - mean) * rstd * g0.y + b0.y;
+                o[2] = (f[i][2] - mean) * rstd * g0.z + b0.z; o[3] = (f[i][3] - mean) * rstd * g0.w + b0.w;
+                o[4] = (f[i][4] - mean) * rstd * g1.x + b1.x; o[5] = (f[i][5] - mean) * rstd * g1.y + b1.y;
+                o[6] = (f[i][6] - mean) * rstd * g1.z + b1.z; o[7] = (f[i][7] - mean) * rstd * g1.w + b1.w;
+                *reinterpret_cast<uint4*>(y + t * ypitch + c) = pack8(o);
+            }
+        }
+    }
+}
+
+static int grid_for(long work_items, int per_block) {
+    long g = (work_items + per_block - 1) / per_block;
+    long cap = (long)num_sms() * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+static bool view_ok_bf16(const skb_view* v) {
+    return v && v->ptr && v->dtype == SKB_BF16 && v->c % 8 == 0 && v->pitch % 8 == 0 && v->c <= v->pitch && ((uintptr_t)v->ptr & 15) == 0 &&
+           v->n > 0 && v->h > 0 && v->w > 0;
+}
+
+}  // namespace skb
+
+using namespace skb;
+
+extern "C" int skb_focus_nchw_f32(const float* img, int32_t n, int32_t h, int32_t w, const skb_view* y, void* stream) {
+    int rc = check_device();
+    if (rc != SKB_OK) return rc;
+    SKB_REQUIRE(img && view_ok_bf16(y), SKB_ERR_ARG, "focus: bad arguments");
+    SKB_REQUIRE(h % 2 == 0 && w % 2 == 0 && ((uintptr_t)img & 7) == 0, SKB_ERR_ARG, "focus: H, W must be even (got %dx%d)", h, w);
+    SKB_REQUIRE(y->n == n && y->h == h / 2 && y->w == w / 2 && y->c >= 16, SKB_ERR_ARG, "focus: output view mismatch");
+    const long total = (long)n * (h / 2) * (w / 2);
+    focus_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, n, h, w, (__nv_bfloat16*)y->ptr, y->pitch, y->c);
+    SKB_LAUNCH_CHECK();
+    return SKB_OK;
+}
+
+extern "C" int skb_maxpool5_bf16(const skb_view* x, const skb_view* y, void* stream) {
+    int rc = check_device();
+    if (rc != SKB_OK) return rc;
+    SKB_REQUIRE(view_ok_bf16(x) && view_ok_bf16(y), SKB_ERR_ARG, "maxpool5: bad view");
+    SKB_REQUIRE(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c, SKB_ERR_ARG, "maxpool5: shape mismatch");
+    const long total = (long)x->n * x->h * x->w * (x->c / 8);
+    maxpool5_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x->ptr, x->pitch, (__nv_bfloat16*)y->ptr,
+                                                                             y->pitch, x->n, x->h, x->w, x->c / 8);
+    SKB_LAUNCH_CHECK();
+    return SKB_OK;
+}
+
+static int cbam_slabs(int hw) { int s = (hw + 255) / 256; return s < 1 ? 1 : (s > 64 ? 64 : s); }
+
+extern "C" size_t skb_cbam_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t c) {
+    const size_t slabs = cbam_slabs(h * w);
+    return sizeof(float) * ((size_t)2 * n * slabs * c + (size_t)n * c + (size_t)2 * n * h * w) + 64;
+}
+
+extern "C" int skb_cbam_bf16(const skb_view* x, const float* w0, const float* w1, int32_t reduced, const float* w7, const skb_view* y,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_device();
+    if (rc != SKB_OK) return rc;
+    SKB_REQUIRE(view_ok_bf16(x) && view_ok_bf16(y) && w0 && w1 && w7 && workspace, SKB_ERR_ARG, "cbam: bad arguments");
+    SKB_REQUIRE(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c, SKB_ERR_ARG, "cbam: shape mismatch");
+    const int N = x->n, H = x->h, W = x->w, C = x->c, HW = H * W;
+    SKB_REQUIRE(C / 8 <= 256 && reduced >= 1 && reduced <= 256, SKB_ERR_UNSUPPORTED, "cbam: C=%d reduced=%d", C, reduced);
+    SKB_REQUIRE(workspace_bytes >= skb_cbam_workspace_bytes(N, H, W, C), SKB_ERR_WORKSPACE, "cbam: workspace too small");
+    const int slabs = cbam_slabs(HW);
+    float* psum = (float*)workspace;
+    float* pmax = psum + (size_t)N * slabs * C;
+    float* att = pmax + (size_t)N * slabs * C;
+    float* stats = att + (size_t)N * C;
+    stats = (float*)(((uintptr_t)stats + 15) & ~(uintptr_t)15);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int C8 = C / 8;
+    const int lanes = 256 / C8;
+    cbam_pool_kernel<<<dim3(slabs, N), 256, sizeof(float) * 2 * lanes * C, st>>>((const __nv_bfloat16*)x->ptr, x->pitch, HW, C, slabs, psum, pmax);
+    SKB_LAUNCH_CHECK();
+    cbam_mlp_kernel<<<N, 256, sizeof(float) * (2 * C + 2 * reduced), st>>>(psum, pmax, slabs, HW, C, reduced, w0, w1, att);
+    SKB_LAUNCH_CHECK();
+    const long npix = (long)N * HW;
+    cbam_stats_kernel<<<grid_for(npix, 8), 256, 0, st>>>((const __nv_bfloat16*)x->ptr, x->pitch, att, npix, HW, C, stats);
+    SKB_LAUNCH_CHECK();
+    cbam_apply_kernel<<<grid_for(npix, 8), 256, 0, st>>>((const __nv_bfloat16*)x->ptr, x->pitch, att, stats, w7, N, H, W, C,
+                                                        (__nv_bfloat16*)y->ptr, y->pitch);
+    SKB_LAUNCH_CHECK();
+    return SKB_OK;
+}
+
+extern "C" size_t skb_cla_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t heads) {
+    return sizeof(float) * ((size_t)n * heads * h * w + (size_t)2 * n * heads * w) + 64;
+}
+
+extern "C" int skb_cla_core_bf16(const skb_view* q, const skb_view* k, const skb_view* v, const skb_view* o, int32_t heads, float scale,
+                                 float r2, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_device();
+    if (rc != SKB_OK) return rc;
+    SKB_REQUIRE(view_ok_bf16(q) && view_ok_bf16(k) && view_ok_bf16(v) && view_ok_bf16(o) && workspace, SKB_ERR_ARG, "cla: bad arguments");
+    SKB_REQUIRE(k->c == q->c && v->n == k->n && v->h == k->h && v->w == k->w && k->n == q->n, SKB_ERR_ARG, "cla: q/k/v mismatch");
+    SKB_REQUIRE(o->n == q->n && o->h == q->h && o->w == q->w && o->c == v->c, SKB_ERR_ARG, "cla: output mismatch");
+    SKB_REQUIRE(heads >= 1 && heads <= 32 && q->c % heads == 0 && v->c % heads == 0 && (q->c / heads) % 8 == 0 && (v->c / heads) % 8 == 0 &&
+                    q->c / heads <= 256 && 256 % (q->c / heads) == 0,
+                SKB_ERR_UNSUPPORTED, "cla: heads=%d Cq=%d Cv=%d", heads, q->c, v->c);
+    const int N = q->n, H = q->h, W = q->w;
+    SKB_REQUIRE(workspace_bytes >= skb_cla_workspace_bytes(N, H, W, heads), SKB_ERR_WORKSPACE, "cla: workspace too small");
+    float* s = (float*)workspace;
+    float* st = s + (size_t)N * heads * H * W;
+    st = (float*)(((uintptr_t)st + 15) & ~(uintptr_t)15);
+    cudaStream_t cs = (cudaStream_t)stream;
+    const long npix = (long)N * H * W;
+    cla_score_kernel<<<grid_for(npix, 8), 256, 0, cs>>>((const __nv_bfloat16*)q->ptr, q->pitch, (const __nv_bfloat16*)k->ptr, k->pitch, N, H, W,
+                                                       k->h, k->w, q->c, heads, scale, s);
+    SKB_LAUNCH_CHECK();
+    cla_colstat_kernel<<<grid_for((long)N * heads * W, 128), 128, 0, cs>>>(s, N * heads, H, W, st);
+    SKB_LAUNCH_CHECK();
+    cla_apply_kernel<<<grid_for(npix, 8), 256, 0, cs>>>(s, st, (const __nv_bfloat16*)v->ptr, v->pitch, N, H, W, v->h, v->w, v->c, heads, r2,
+                                                       (__nv_bfloat16*)o->ptr, o->pitch);
+    SKB_LAUNCH_CHECK();
+    return SKB_OK;
+}
+
+extern "C" int skb_layernorm_bf16(const skb_view* x, const float* gamma, const float* beta, float eps, const skb_view* y, void* stream) {
+    int rc = check_device();
+    if (rc != SKB_OK) return rc;
+    SKB_REQUIRE(view_ok_bf16(x) && view_ok_bf16(y) && gamma && beta, SKB_ERR_ARG, "layernorm: bad arguments");
+    SKB_REQUIRE(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c, SKB_ERR_ARG, "layernorm: shape mismatch");
+    SKB_REQUIRE(x->c <= 2048, SKB_ERR_UNSUPPORTED, "layernorm: C=%d > 2048", x->c);
+    const long ntok = (long)x->n * x->h * x->w;
+    layernorm_kernel<<<grid_for(ntok, 8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x->ptr, x->pitch, gamma, beta, eps, ntok, x->c,
+                                                                         (__nv_bfloat16*)y->ptr, y->pitch);
+    SKB_LAUNCH_CHECK();
+    return SKB_OK;
+}

@@ -1,0 +1,388 @@
+// NMS kernels.
+//
+// (1) skb_nms_f32: torchvision.ops.nms semantics (call site skyeye/utils/metrics.py:442), bit-exact
+//     with the CPU op: stable descending radix sort, 64x64 IoU bitmask tiles built with explicit
+//     round-to-nearest intrinsics (no FMA contraction, true division), sequential greedy reduce.
+// (2) skb_nms_batched_f32: the whole wrapper non_max_suppression (metrics.py:361-457) for a batch
+//     without host synchronisation.  Candidate rows are emitted as 64-bit sort keys
+//     [image | ~score | slot] so one radix sort orders every image by (score desc, row asc) =
+//     the reference's boolean-mask order + torchvision's stable sort.  Greedy suppression then
+//     only ever compares a candidate with boxes that were KEPT before it, and the wrapper keeps at
+//     most max_det of them (metrics.py:443-444), so each image needs <= n*max_det IoU tests instead of
+//     n^2/2: one CTA per image walks the sorted candidates in chunks with the kept list in shared
+//     memory (warp-ballot compaction, no n x n mask in HBM).
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace skb {
+
+__device__ __forceinline__ float box_area(float x1, float y1, float x2, float y2) { return __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1)); }
+// iou(i, j) > thr exactly as torchvision's CPU kernel evaluates it
+__device__ __forceinline__ bool iou_gt(float ax1, float ay1, float ax2, float ay2, float aarea, float bx1, float by1, float bx2, float by2,
+                                       float barea, float thr) {
+    const float xx1 = fmaxf(ax1, bx1), yy1 = fmaxf(ay1, by1);
+    const float xx2 = fminf(ax2, bx2), yy2 = fminf(ay2, by2);
+    const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+    const float inter = __fmul_rn(w, h);
+    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, barea), inter));
+    return ovr > thr;  // NaN (0/0) never suppresses
+}
+
+// =============================================================================================
+// (1) generic bit-exact NMS
+// =============================================================================================
+__global__ void iota_kernel(int* idx, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) idx[i] = i;
+}
+__global__ void gather_boxes_kernel(const float4* __restrict__ boxes, const int* __restrict__ order, int n, float4* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = boxes[order[i]];
+}
+// mask[i][cb] bit j: iou(sorted i, sorted cb*64 + j) > thr, only for column blocks >= row block
+__global__ void nms_mask_kernel(const float4* __restrict__ sb, int n, float thr, int col_blocks, unsigned long long* __restrict__ mask) {
+    const int rb = blockIdx.y, cb = blockIdx.x;
+    if (cb < rb) return;
+    __shared__ float4 cbox[64];
+    const int cn = min(64, n - cb * 64);
+    if (threadIdx.x < cn) cbox[threadIdx.x] = sb[cb * 64 + threadIdx.x];
+    __syncthreads();
+    const int i = rb * 64 + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = sb[i];
+    const float aarea = box_area(a.x, a.y, a.z, a.w);
+    unsigned long long bits = 0;
+    const int j0 = (rb == cb) ? threadIdx.x + 1 : 0;
+    for (int j = j0; j < cn; ++j) {
+        const float4 b = cbox[j];
+        if (iou_gt(a.x, a.y, a.z, a.w, aarea, b.x, b.y, b.z, b.w, box_area(b.x, b.y, b.z, b.w), thr)) bits |= 1ULL << j;
+    }
+    mask[(size_t)i * col_blocks + cb] = bits;
+}
+// sequential greedy reduce over the mask (single CTA); writes kept ORIGINAL indices in score order
+__global__ void nms_reduce_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ order, int n, int col_blocks,
+                                  long long* __restrict__ keep, int* __restrict__ n_keep) {
+    extern __shared__ unsigned long long remv[];
+    for (int j = threadIdx.x; j < col_blocks; j += blockDim.x) remv[j] = 0ULL;
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    for (int i = 0; i < n; ++i) {
+        const int nb = i >> 6, ib = i & 63;
+        const bool alive = !((remv[nb] >> ib) & 1ULL);
+        __syncthreads();  // everyone has read remv[nb] before it is updated
+        if (alive) {
+            if (threadIdx.x == 0) keep[cnt++] = (long long)order[i];
+            const unsigned long long* row = mask + (size_t)i * col_blocks;
+            for (int j = nb + threadIdx.x; j < col_blocks; j += blockDim.x) remv[j] |= row[j];
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) *n_keep = cnt;
+}
+
+struct NmsWs {
+    float* keys_out;
+    int* idx_in;
+    int* idx_out;
+    float4* sboxes;
+    unsigned long long* mask;
+    void* cub_tmp;
+    size_t cub_bytes;
+};
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+static size_t nms_layout(int n, void* base, NmsWs* ws) {
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, cub_bytes, (const float*)nullptr, (float*)nullptr, (const int*)nullptr, (int*)nullptr, n);
+    const int cbk = (n + 63) / 64;
+    size_t off = 0;
+    uint8_t* b = (uint8_t*)base;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return b ? (void*)(b + o) : nullptr; };
+    void* k = take(sizeof(float) * n);
+    void* i0 = take(sizeof(int) * n);
+    void* i1 = take(sizeof(int) * n);
+    void* sb = take(sizeof(float4) * n);
+    void* m = take(sizeof(unsigned long long) * (size_t)n * cbk);
+    void* c = take(cub_bytes);
+    if (ws) { ws->keys_out = (float*)k; ws->idx_in = (int*)i0; ws->idx_out = (int*)i1; ws->sboxes = (float4*)sb; ws->mask = (unsigned long long*)m; ws->cub_tmp = c; ws->cub_bytes = cub_bytes; }
+    return off + 256;
+}
+
+// =============================================================================================
+// (2) batched wrapper
+// =============================================================================================
+constexpr int KEY_SLOT_BITS = 22;
+constexpr int KEY_IMG_BITS = 10;
+constexpr int MAX_NMS_BOXES = 30000;  // metrics.py:393
+constexpr int NMS_THREADS = 256;
+constexpr int NMS_MAX_KEEP = 1536;
+
+struct FilterParams {
+    const float* pred;
+    int B, N, nc, no;
+    float conf;
+    int multi_label, compat;
+    int n_classes;
+    float classes[32];
+};
+
+__device__ __forceinline__ unsigned int desc_bits(float s) {
+    unsigned int u = __float_as_uint(s);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending-orderable
+    return ~u;                                       // descending
+}
+__device__ __forceinline__ bool class_pass(const FilterParams& p, float col5) {
+    if (p.n_classes <= 0) return true;
+    for (int i = 0; i < p.n_classes; ++i)
+        if (col5 == p.classes[i]) return true;
+    return false;
+}
+
+// One thread per (image, box). Emits sort keys of surviving rows; order-free (the key is total).
+__global__ void nms_filter_kernel(const FilterParams p, unsigned long long* __restrict__ keys, unsigned int* __restrict__ total,
+                                  int* __restrict__ count) {
+    const long nbox = (long)p.B * p.N;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nbox; i += (long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / p.N), r = (int)(i % p.N);
+        const float* x = p.pred + i * p.no;
+        const float obj = x[4];
+        if (!(obj > p.conf)) continue;  // metrics.py:391,402
+        auto emit = [&](float score, int slot) {
+            const unsigned int pos = atomicAdd(total, 1u);
+            atomicAdd(count + b, 1);
+            keys[pos] = ((unsigned long long)b << (32 + KEY_SLOT_BITS)) | ((unsigned long long)desc_bits(score) << KEY_SLOT_BITS) |
+                        (unsigned long long)slot;
+        };
+        if (p.nc > 1 || (p.compat == 1 && p.nc == 1)) {
+            if (p.multi_label) {  // metrics.py:407-410: one row per (box, class) above the threshold
+                for (int j = 0; j < p.nc; ++j) {
+                    const float cp = x[5 + j];
+                    const float conf = p.compat ? __fmul_rn(cp, obj) : cp;
+                    if (conf > p.conf && class_pass(p, p.compat ? (float)j : cp)) emit(p.compat ? conf : obj, r * p.nc + j);
+                }
+            } else {  // metrics.py:411-414: best class (first maximum)
+                float best = x[5];
+                int bj = 0;
+                if (p.compat) best = __fmul_rn(best, obj);
+                for (int j = 1; j < p.nc; ++j) {
+                    float cp = x[5 + j];
+                    if (p.compat) cp = __fmul_rn(cp, obj);
+                    if (cp > best) { best = cp; bj = j; }
+                }
+                if (best > p.conf && class_pass(p, p.compat ? (float)bj : best)) emit(p.compat ? best : obj, r * p.nc + bj);
+            }
+        } else {  // nc == 1 (metrics.py:415-419): row [cx,cy,w,h,obj,0]; nc == 0 in fixed mode
+            if (class_pass(p, 0.0f)) emit(obj, r);
+        }
+    }
+}
+
+struct BatchedParams {
+    const float* pred;
+    int B, N, nc, no;
+    float iou;
+    int agnostic, multi_label, compat, max_det;
+    int capacity;
+};
+
+struct Cand {
+    float x1, y1, x2, y2, area;
+    float row[7];
+};
+
+__device__ __forceinline__ void load_cand(const BatchedParams& p, int b, unsigned long long key, Cand& c) {
+    const int slot = (int)(key & ((1ULL << KEY_SLOT_BITS) - 1));
+    int r, j;
+    const bool per_class = p.nc > 1 || (p.compat == 1 && p.nc == 1);
+    if (per_class) { r = slot / p.nc; j = slot - r * p.nc; } else { r = slot; j = 0; }
+    const float* x = p.pred + ((long)b * p.N + r) * p.no;
+    const float cx = x[0], cy = x[1], w = x[2], h = x[3], obj = x[4];
+    if (p.compat == 0) {
+        const float col5 = p.nc > 1 ? x[5 + j] : 0.0f;
+        c.row[0] = cx; c.row[1] = cy; c.row[2] = w; c.row[3] = h; c.row[4] = obj; c.row[5] = col5; c.row[6] = (float)j;
+        // quirk X8: offset = column 5 (class PROBABILITY) * 4096, boxes = raw (cx,cy,w,h) + offset (metrics.py:435-436)
+        const float off = p.agnostic ? 0.0f : __fmul_rn(col5, 4096.0f);
+        c.x1 = __fadd_rn(cx, off); c.y1 = __fadd_rn(cy, off); c.x2 = __fadd_rn(w, off); c.y2 = __fadd_rn(h, off);
+    } else {
+        const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+        const float bx1 = __fsub_rn(cx, hw), by1 = __fsub_rn(cy, hh), bx2 = __fadd_rn(cx, hw), by2 = __fadd_rn(cy, hh);
+        const float conf = per_class ? __fmul_rn(x[5 + j], obj) : obj;
+        c.row[0] = bx1; c.row[1] = by1; c.row[2] = bx2; c.row[3] = by2; c.row[4] = conf; c.row[5] = (float)j; c.row[6] = 0.0f;
+        const float off = p.agnostic ? 0.0f : __fmul_rn((float)j, 4096.0f);
+        c.x1 = __fadd_rn(bx1, off); c.y1 = __fadd_rn(by1, off); c.x2 = __fadd_rn(bx2, off); c.y2 = __fadd_rn(by2, off);
+    }
+    c.area = box_area(c.x1, c.y1, c.x2, c.y2);
+}
+
+// grid = B images, 256 threads. Sorted keys of image b are the segment [off_b, off_b + cnt_b).
+__global__ void __launch_bounds__(NMS_THREADS)
+nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict__ keys, const int* __restrict__ count,
+                    float* __restrict__ out, int* __restrict__ out_count) {
+    __shared__ float kx1[NMS_MAX_KEEP], ky1[NMS_MAX_KEEP], kx2[NMS_MAX_KEEP], ky2[NMS_MAX_KEEP], kar[NMS_MAX_KEEP];
+    __shared__ int surv[NMS_THREADS];   // chunk-local ids of phase-A survivors, in order
+    __shared__ int warp_cnt[NMS_THREADS / 32];
+    __shared__ int s_nsurv, s_kept;
+    __shared__ float cx1[NMS_THREADS], cy1[NMS_THREADS], cx2[NMS_THREADS], cy2[NMS_THREADS], car[NMS_THREADS];
+    __shared__ float crow[NMS_THREADS][7];
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long off = 0;
+    for (int i = 0; i < b; ++i) off += count[i];
+    int n = count[b];
+    if (n > MAX_NMS_BOXES) n = MAX_NMS_BOXES;  // metrics.py:431-432 (sorted order => top-30000 by score)
+    if (tid == 0) s_kept = 0;
+    __syncthreads();
+
+    for (int base = 0; base < n; base += NMS_THREADS) {
+        const int kept0 = s_kept;
+        if (kept0 >= p.max_det) break;
+        const int i = base + tid;
+        bool alive = i < n;
+        Cand c;
+        if (alive) {
+            load_cand(p, b, keys[off + i], c);
+            // phase A: against everything kept in earlier chunks (parallel over candidates)
+            for (int k = 0; k < kept0; ++k)
+                if (iou_gt(kx1[k], ky1[k], kx2[k], ky2[k], kar[k], c.x1, c.y1, c.x2, c.y2, c.area, p.iou)) { alive = false; break; }
+        }
+        // order-preserving compaction of survivors
+        const unsigned int bal = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int wbase = 0;
+        for (int wj = 0; wj < warp; ++wj) wbase += warp_cnt[wj];
+        if (alive) {
+            const int pos = wbase + __popc(bal & ((1u << lane) - 1u));
+            surv[pos] = tid;
+        }
+        if (tid == NMS_THREADS - 1) s_nsurv = wbase + __popc(bal);
+        cx1[tid] = c.x1; cy1[tid] = c.y1; cx2[tid] = c.x2; cy2[tid] = c.y2; car[tid] = c.area;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) crow[tid][q] = c.row[q];
+        __syncthreads();
+        // phase B: survivors in order, one warp, each against the boxes kept within THIS chunk
+        if (warp == 0) {
+            const int ns = s_nsurv;
+            int kept = kept0;
+            for (int s = 0; s < ns && kept < p.max_det; ++s) {
+                const int t = surv[s];
+                const float ax1 = cx1[t], ay1 = cy1[t], ax2 = cx2[t], ay2 = cy2[t], aar = car[t];
+                bool sup = false;
+                for (int k = kept0 + lane; k < kept; k += 32)
+                    if (iou_gt(kx1[k], ky1[k], kx2[k], ky2[k], kar[k], ax1, ay1, ax2, ay2, aar, p.iou)) { sup = true; break; }
+                if (!__any_sync(0xffffffffu, sup)) {
+                    if (lane == 0) { kx1[kept] = ax1; ky1[kept] = ay1; kx2[kept] = ax2; ky2[kept] = ay2; kar[kept] = aar; }
+                    if (lane < 7) out[((long)b * p.max_det + kept) * 7 + lane] = crow[t][lane];
+                    ++kept;
+                    __syncwarp();
+                }
+            }
+            if (lane == 0) s_kept = kept;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) out_count[b] = s_kept;
+}
+
+struct BatchedWs {
+    unsigned long long* keys_in;
+    unsigned long long* keys_out;
+    unsigned int* total;
+    int* count;
+    void* cub_tmp;
+    size_t cub_bytes;
+};
+static size_t batched_layout(int B, int N, int nc, int multi_label, void* base, BatchedWs* ws) {
+    const size_t cap = (size_t)B * N * ((multi_label && nc > 1) ? nc : 1);
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (long)cap);
+    size_t off = 0;
+    uint8_t* b = (uint8_t*)base;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return b ? (void*)(b + o) : nullptr; };
+    void* k0 = take(8 * cap);
+    void* k1 = take(8 * cap);
+    void* cnt = take(sizeof(int) * (B + 1));
+    void* c = take(cub_bytes);
+    if (ws) { ws->keys_in = (unsigned long long*)k0; ws->keys_out = (unsigned long long*)k1; ws->count = (int*)cnt + 1; ws->total = (unsigned int*)cnt; ws->cub_tmp = c; ws->cub_bytes = cub_bytes; }
+    return off + 256;
+}
+
+}  // namespace skb
+
+using namespace skb;
+
+extern "C" size_t skb_nms_workspace_bytes(int32_t n) { return n <= 0 ? 256 : nms_layout(n, nullptr, nullptr); }
+
+extern "C" int skb_nms_f32(const float* boxes, const float* scores, int32_t n, float iou_thr, int64_t* keep, int32_t* n_keep, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+    int rc = check_device();
+    if (rc != SKB_OK) return rc;
+    SKB_REQUIRE(n >= 0 && keep && n_keep, SKB_ERR_ARG, "nms: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) {
+        SKB_CUDA(cudaMemsetAsync(n_keep, 0, sizeof(int), st));
+        return SKB_OK;
+    }
+    SKB_REQUIRE(boxes && scores && workspace && ((uintptr_t)boxes & 15) == 0, SKB_ERR_ARG, "nms: null or unaligned boxes");
+    SKB_REQUIRE(workspace_bytes >= skb_nms_workspace_bytes(n), SKB_ERR_WORKSPACE, "nms: workspace %zu < %zu", workspace_bytes, skb_nms_workspace_bytes(n));
+    NmsWs ws;
+    nms_layout(n, workspace, &ws);
+    const int cbk = (n + 63) / 64;
+    iota_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws.idx_in, n);
+    SKB_LAUNCH_CHECK();
+    SKB_CUDA(cub::DeviceRadixSort::SortPairsDescending(ws.cub_tmp, ws.cub_bytes, scores, ws.keys_out, ws.idx_in, ws.idx_out, n, 0, 32, st));
+    gather_boxes_kernel<<<(n + 255) / 256, 256, 0, st>>>((const float4*)boxes, ws.idx_out, n, ws.sboxes);
+    SKB_LAUNCH_CHECK();
+    nms_mask_kernel<<<dim3(cbk, cbk), 64, 0, st>>>(ws.sboxes, n, iou_thr, cbk, ws.mask);
+    SKB_LAUNCH_CHECK();
+    const size_t sh = sizeof(unsigned long long) * cbk;
+    SKB_REQUIRE(sh <= 48 * 1024, SKB_ERR_UNSUPPORTED, "nms: n=%d too large for the single-CTA reduce", n);
+    nms_reduce_kernel<<<1, 256, sh, st>>>(ws.mask, ws.idx_out, n, cbk, (long long*)keep, n_keep);
+    SKB_LAUNCH_CHECK();
+    return SKB_OK;
+}
+
+extern "C" size_t skb_nms_batched_workspace_bytes(int32_t b, int32_t n, int32_t nc, int32_t multi_label) {
+    if (b <= 0 || n <= 0) return 256;
+    return batched_layout(b, n, nc, multi_label, nullptr, nullptr);
+}
+
+extern "C" int skb_nms_batched_f32(const float* pred, int32_t b, int32_t n, int32_t nc, float conf_thr, float iou_thr,
+                                   const int32_t* classes_host, int32_t n_classes, int32_t agnostic, int32_t multi_label, int32_t max_det,
+                                   int32_t compat, float* out, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_device();
+    if (rc != SKB_OK) return rc;
+    SKB_REQUIRE(pred && out && out_count && workspace && b > 0 && n > 0 && nc >= 0, SKB_ERR_ARG, "nms_batched: bad arguments");
+    SKB_REQUIRE(compat == 0 || compat == 1, SKB_ERR_ARG, "nms_batched: compat must be 0 (reference) or 1 (fixed)");
+    SKB_REQUIRE(max_det >= 1 && max_det <= NMS_MAX_KEEP, SKB_ERR_UNSUPPORTED, "nms_batched: max_det=%d (supported: 1..%d)", max_det, NMS_MAX_KEEP);
+    SKB_REQUIRE(b <= (1 << KEY_IMG_BITS) && (long)n * (nc > 1 ? nc : 1) <= (1L << KEY_SLOT_BITS), SKB_ERR_UNSUPPORTED,
+                "nms_batched: B=%d N*nc=%ld exceed the sort-key fields", b, (long)n * (nc > 1 ? nc : 1));
+    SKB_REQUIRE(n_classes <= 32, SKB_ERR_UNSUPPORTED, "nms_batched: at most 32 class filters");
+    multi_label = (multi_label && nc > 1) ? 1 : 0;  // metrics.py:396
+    SKB_REQUIRE(workspace_bytes >= skb_nms_batched_workspace_bytes(b, n, nc, multi_label), SKB_ERR_WORKSPACE, "nms_batched: workspace too small");
+    BatchedWs ws;
+    batched_layout(b, n, nc, multi_label, workspace, &ws);
+    const size_t cap = (size_t)b * n * (multi_label ? nc : 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    SKB_CUDA(cudaMemsetAsync(ws.keys_in, 0xFF, 8 * cap, st));
+    SKB_CUDA(cudaMemsetAsync(ws.total, 0, sizeof(int) * (b + 1), st));
+    FilterParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.pred = pred; fp.B = b; fp.N = n; fp.nc = nc; fp.no = nc + 5; fp.conf = conf_thr; fp.multi_label = multi_label; fp.compat = compat;
+    fp.n_classes = classes_host ? n_classes : 0;
+    for (int i = 0; i < fp.n_classes; ++i) fp.classes[i] = (float)classes_host[i];
+    const long nbox = (long)b * n;
+    long g = (nbox + 255) / 256;
+    const long gcap = (long)num_sms() * 16;
+    nms_filter_kernel<<<(int)(g > gcap ? gcap : g), 256, 0, st>>>(fp, ws.keys_in, ws.total, ws.count);
+    SKB_LAUNCH_CHECK();
+    int img_bits = 1;
+    while ((1 << img_bits) < b) ++img_bits;
+    SKB_CUDA(cub::DeviceRadixSort::SortKeys(ws.cub_tmp, ws.cub_bytes, ws.keys_in, ws.keys_out, (long)cap, 0, 32 + KEY_SLOT_BITS + img_bits, st));
+    BatchedParams bp;
+    bp.pred = pred; bp.B = b; bp.N = n; bp.nc = nc; bp.no = nc + 5; bp.iou = iou_thr; bp.agnostic = agnostic; bp.multi_label = multi_label;
+    bp.compat = compat; bp.max_det = max_det; bp.capacity = (int)cap;
+    nms_keptlist_kernel<<<b, NMS_THREADS, 0, st>>>(bp, ws.keys_out, ws.count, out, out_count);
+    SKB_LAUNCH_CHECK();
+    return SKB_OK;
+}

@@ -1,0 +1,246 @@
+"""Host-side execution engine: NHWC views over torch-owned buffers, weight preparation (BN folding,
+bf16 packing into the implicit-GEMM layout) and a static launch plan per input shape.
+
+PyTorch is plumbing here (device memory, streams); every op appended to a plan is one call into
+libskyeye_b200.so.  A plan owns all intermediate buffers, takes no host synchronisation while it
+runs and can therefore be captured into a CUDA graph (``Plan.capture``).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Callable, List, Optional, Sequence
+
+import torch
+
+from . import _native as N
+from ._native import ACT_NONE, ACT_RELU, ACT_SILU, SKB_BF16, SKB_F32, skb_view
+
+BN_EPS = 1e-5
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class View:
+    """Channel slice [c0, c0+c) of an NHWC torch buffer [n, h, w, pitch]."""
+    __slots__ = ("t", "n", "h", "w", "c", "c0", "pitch", "dtype", "_s")
+
+    def __init__(self, t: torch.Tensor, c0: int = 0, c: Optional[int] = None):
+        assert t.dim() == 4 and t.is_contiguous()
+        self.t = t
+        self.n, self.h, self.w, self.pitch = t.shape
+        self.c0 = c0
+        self.c = self.pitch - c0 if c is None else c
+        assert 0 <= c0 and self.c0 + self.c <= self.pitch
+        self.dtype = SKB_BF16 if t.dtype == torch.bfloat16 else SKB_F32
+        assert t.dtype in (torch.bfloat16, torch.float32)
+        self._s = skb_view(t.data_ptr() + c0 * t.element_size(), self.n, self.h, self.w, self.c, self.pitch, self.dtype)
+
+    def slice(self, c0: int, c1: int) -> "View":
+        return View(self.t, self.c0 + c0, c1 - c0)
+
+    @property
+    def ref(self):
+        return ctypes.byref(self._s)
+
+    def torch(self) -> torch.Tensor:
+        """[n, h, w, c] torch view (no copy)."""
+        return self.t[..., self.c0:self.c0 + self.c]
+
+    def nchw(self) -> torch.Tensor:
+        return self.torch().permute(0, 3, 1, 2)
+
+
+def new_buffer(n, h, w, c, dtype=torch.bfloat16, device="cuda") -> View:
+    return View(torch.empty((n, h, w, c), dtype=dtype, device=device))
+
+
+def from_nchw(x: torch.Tensor, dtype=torch.bfloat16) -> View:
+    """Test helper: NCHW tensor -> NHWC buffer view (host-side plumbing, not on the hot path)."""
+    return View(x.permute(0, 2, 3, 1).contiguous().to(dtype))
+
+
+# ----------------------------------------------------------------------------------------------
+# weight preparation
+# ----------------------------------------------------------------------------------------------
+def round_cout(c: int) -> int:
+    return 32 if c <= 32 else (c + 63) // 64 * 64
+
+
+class PackedConv:
+    """bf16 weights [cout_pad, k*k*cin] (K order = (ky, kx, cin): matches the kernel's tap-major
+    K loop) + fp32 bias [cout_pad]; rows >= cout are zero."""
+
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], device="cuda", cin_pad: Optional[int] = None):
+        w = weight.detach().float()
+        if w.dim() == 2:
+            w = w[:, :, None, None]
+        cout, cin, kh, kw = w.shape
+        assert kh == kw
+        cin_p = cin if cin_pad is None else cin_pad
+        self.cout, self.cin, self.k = cout, cin_p, kh
+        self.cout_pad = round_cout(cout)
+        wp = torch.zeros((self.cout_pad, kh, kw, cin_p), dtype=torch.float32)
+        wp[:cout, :, :, :cin] = w.permute(0, 2, 3, 1).cpu()
+        self.w = wp.reshape(self.cout_pad, kh * kw * cin_p).to(device=device, dtype=torch.bfloat16).contiguous()
+        b = torch.zeros(self.cout_pad, dtype=torch.float32)
+        if bias is not None:
+            b[:cout] = bias.detach().float().cpu()
+        self.b = b.to(device)
+
+    @staticmethod
+    def fold_bn(conv_w, bn_w, bn_b, bn_mean, bn_var, eps=BN_EPS):
+        """w' = w*g/sqrt(var+eps), b' = beta - mean*g/sqrt(var+eps) (eval-mode BN, blocks.py:32,38)."""
+        s = bn_w.detach().float() / torch.sqrt(bn_var.detach().float() + eps)
+        return conv_w.detach().float() * s.view(-1, 1, 1, 1), bn_b.detach().float() - bn_mean.detach().float() * s
+
+    @staticmethod
+    def concat(parts: Sequence["PackedConv"]) -> "PackedConv":
+        """Stack several convs that read the same input along Cout (CSP cv1||cv2, CLA k||v)."""
+        p0 = parts[0]
+        assert all(p.cin == p0.cin and p.k == p0.k and p.cout == p.cout_pad for p in parts[:-1]), \
+            "only the last part of a fused conv may have padded output channels"
+        out = PackedConv.__new__(PackedConv)
+        out.cin, out.k = p0.cin, p0.k
+        out.cout = sum(p.cout for p in parts)
+        w = torch.cat([p.w[:p.cout] for p in parts], 0)
+        b = torch.cat([p.b[:p.cout] for p in parts], 0)
+        out.cout_pad = round_cout(out.cout)
+        if out.cout_pad != out.cout:
+            w = torch.cat([w, torch.zeros((out.cout_pad - out.cout, w.shape[1]), dtype=w.dtype, device=w.device)], 0)
+            b = torch.cat([b, torch.zeros(out.cout_pad - out.cout, dtype=b.dtype, device=b.device)], 0)
+        out.w, out.b = w.contiguous(), b.contiguous()
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# eager op wrappers (one native call each)
+# ----------------------------------------------------------------------------------------------
+def conv2d(x: View, pw: PackedConv, y: View, stride: int = 1, act: int = ACT_SILU, residual: Optional[View] = None,
+           upsample2x: bool = False, stream: Optional[int] = None) -> None:
+    assert x.c == pw.cin, (x.c, pw.cin)
+    rc = N.lib().skb_conv2d_bf16(x.ref, pw.w.data_ptr(), pw.b.data_ptr(), residual.ref if residual is not None else None,
+                                 y.ref, pw.cout_pad, pw.k, stride, act, 1 if upsample2x else 0,
+                                 _stream_ptr() if stream is None else stream)
+    N.check(rc, "skb_conv2d_bf16")
+
+
+def focus(img: torch.Tensor, y: View, stream=None) -> None:
+    assert img.dtype == torch.float32 and img.is_contiguous() and img.dim() == 4 and img.shape[1] == 3
+    n, _, h, w = img.shape
+    N.check(N.lib().skb_focus_nchw_f32(img.data_ptr(), n, h, w, y.ref, _stream_ptr() if stream is None else stream), "skb_focus_nchw_f32")
+
+
+def maxpool5(x: View, y: View, stream=None) -> None:
+    N.check(N.lib().skb_maxpool5_bf16(x.ref, y.ref, _stream_ptr() if stream is None else stream), "skb_maxpool5_bf16")
+
+
+def cbam(x: View, w0: torch.Tensor, w1: torch.Tensor, w7: torch.Tensor, y: View, ws: torch.Tensor, stream=None) -> None:
+    N.check(N.lib().skb_cbam_bf16(x.ref, w0.data_ptr(), w1.data_ptr(), w0.shape[0], w7.data_ptr(), y.ref, ws.data_ptr(),
+                                  ws.numel(), _stream_ptr() if stream is None else stream), "skb_cbam_bf16")
+
+
+def cla_core(q: View, k: View, v: View, o: View, heads: int, scale: float, r2: float, ws: torch.Tensor, stream=None) -> None:
+    N.check(N.lib().skb_cla_core_bf16(q.ref, k.ref, v.ref, o.ref, heads, scale, r2, ws.data_ptr(), ws.numel(),
+                                      _stream_ptr() if stream is None else stream), "skb_cla_core_bf16")
+
+
+def layernorm(x: View, gamma: torch.Tensor, beta: torch.Tensor, y: View, eps: float = 1e-5, stream=None) -> None:
+    N.check(N.lib().skb_layernorm_bf16(x.ref, gamma.data_ptr(), beta.data_ptr(), eps, y.ref,
+                                       _stream_ptr() if stream is None else stream), "skb_layernorm_bf16")
+
+
+def flash_attn(qkv: View, o: View, heads: int, scale: float, stream=None) -> None:
+    N.check(N.lib().skb_flash_attn_bf16(qkv.ref, o.ref, heads, scale, _stream_ptr() if stream is None else stream),
+            "skb_flash_attn_bf16")
+
+
+def decode(raws: Sequence[View], na: int, no: int, anchors, in_hw, det: torch.Tensor,
+           raw_out: Optional[Sequence[torch.Tensor]] = None, stream=None) -> None:
+    L = len(raws)
+    arr = (skb_view * L)(*[r._s for r in raws])
+    flat = [float(v) for lvl in anchors for a in lvl for v in a]
+    anc = (ctypes.c_float * len(flat))(*flat)
+    ro = None
+    if raw_out is not None:
+        ro = (ctypes.c_void_p * L)(*[t.data_ptr() for t in raw_out])
+    N.check(N.lib().skb_decode_f32(arr, L, na, no, anc, int(in_hw[0]), int(in_hw[1]), det.data_ptr(), ro,
+                                   _stream_ptr() if stream is None else stream), "skb_decode_f32")
+
+
+def workspace(nbytes: int, device="cuda") -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ----------------------------------------------------------------------------------------------
+# launch plan
+# ----------------------------------------------------------------------------------------------
+class Plan:
+    """Ordered native launches over statically allocated buffers for one input shape."""
+
+    def __init__(self, device="cuda"):
+        self.device = device
+        self.steps: List[Callable[[int], None]] = []
+        self.names: List[str] = []
+        self.keep = []  # buffers / packed weights kept alive
+        self.graph = None
+        self.n_launch_calls = 0
+
+    def buf(self, n, h, w, c, dtype=torch.bfloat16) -> View:
+        v = new_buffer(n, h, w, c, dtype, self.device)
+        self.keep.append(v)
+        return v
+
+    def ws(self, nbytes: int) -> torch.Tensor:
+        t = workspace(nbytes, self.device)
+        self.keep.append(t)
+        return t
+
+    def add(self, name: str, fn: Callable[[int], None]) -> None:
+        self.names.append(name)
+        self.steps.append(fn)
+
+    # -- op builders ---------------------------------------------------------------------------
+    def conv(self, name, x: View, pw: PackedConv, y: View, stride=1, act=ACT_SILU, residual=None, upsample2x=False):
+        self.keep.append(pw)
+        self.add(name, lambda s: conv2d(x, pw, y, stride, act, residual, upsample2x, s))
+        return y
+
+    def run(self, stream: Optional[int] = None) -> None:
+        s = _stream_ptr() if stream is None else stream
+        for fn in self.steps:
+            fn(s)
+
+    def run_timed(self):
+        """Per-step CUDA-event timing (profiling aid): list of (name, ms)."""
+        evs = []
+        s = _stream_ptr()
+        for fn in self.steps:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(s)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return [(n, a.elapsed_time(b)) for n, (a, b) in zip(self.names, evs)]
+
+    def capture(self) -> None:
+        """Capture the whole plan into a CUDA graph (tensor maps are baked in as kernel params)."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run()
+        self.graph = g
+
+    def replay(self) -> None:
+        if self.graph is None:
+            self.run()
+        else:
+            self.graph.replay()

@@ -1,0 +1,164 @@
+"""Parity of the HBM-bound kernels and the flash-attention kernel (through the C ABI) against the
+CPU oracle (oracle/model.py) on identical seeded inputs.  Inputs are bf16-representable; outputs
+are stored in bf16 by these kernels, so the stated bound is one bf16 rounding (2^-8) on top of the
+1e-3 fp32-accumulate tolerance: <= 6e-3 relative to max |reference| (decode is fp32: <= 1e-5)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cases
+from gpu_util import bf16r, randn, rel_err
+from oracle import model as om
+
+pytestmark = pytest.mark.gpu
+TOL = 6e-3
+
+
+def test_focus_space_to_depth_bit_exact():
+    from skyeye import engine as E
+    img = cases.image((2, 3, 32, 48)).cuda()
+    y = E.new_buffer(2, 16, 24, 32)
+    y.t.fill_(1.0)
+    E.focus(img, y)
+    torch.cuda.synchronize()
+    x = img.cpu()
+    ref = torch.cat([x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]], 1)  # blocks.py:174-181
+    got = y.nchw().float().cpu()
+    assert torch.equal(got[:, :12], bf16r(ref))
+    assert bool((got[:, 12:] == 0).all())
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 20, 20), (1, 256, 7, 9), (2, 32, 40, 40)])
+def test_maxpool5_cascade_equals_spp_pools_bit_exact(shape):
+    from skyeye import engine as E
+    x = bf16r(randn(("mp", shape), shape))
+    n, c, h, w = shape
+    cat = torch.zeros((n, h, w, 4 * c), dtype=torch.bfloat16, device="cuda")
+    cat[..., :c] = x.permute(0, 2, 3, 1).to(torch.bfloat16).cuda()
+    for i in range(3):
+        E.maxpool5(E.View(cat, i * c, c), E.View(cat, (i + 1) * c, c))
+    torch.cuda.synchronize()
+    for i, k in enumerate((5, 9, 13)):  # blocks.py:143-149
+        ref = F.max_pool2d(x, k, 1, k // 2)
+        got = cat[..., (i + 1) * c:(i + 2) * c].permute(0, 3, 1, 2).float().cpu()
+        assert torch.equal(got, ref), k
+
+
+@pytest.mark.parametrize("shape", [(2, 256, 20, 20), (1, 512, 40, 24), (3, 64, 9, 11)])
+def test_cbam_matches_oracle(shape):
+    from skyeye import engine as E
+    n, c, h, w = shape
+    r = max(c // 16, 1)
+    x = bf16r(randn(("cbx", shape), shape))
+    sd = {"p.channel_attention.shared_mlp.0.weight": randn(("cb0", shape), (r, c), 0.1),
+          "p.channel_attention.shared_mlp.2.weight": randn(("cb1", shape), (c, r), 0.1),
+          "p.spatial_attention.conv.weight": randn(("cb7", shape), (1, 2, 7, 7), 0.2)}
+    ref = om.cbam(x, sd, "p")
+    xv = E.from_nchw(x.cuda())
+    y = E.new_buffer(n, h, w, c)
+    ws = E.workspace(E.N.lib().skb_cbam_workspace_bytes(n, h, w, c))
+    E.cbam(xv, sd["p.channel_attention.shared_mlp.0.weight"].cuda(), sd["p.channel_attention.shared_mlp.2.weight"].cuda(),
+           sd["p.spatial_attention.conv.weight"].cuda().contiguous(), y, ws)
+    torch.cuda.synchronize()
+    assert rel_err(y.nchw(), ref) < TOL
+
+
+@pytest.mark.parametrize("cq,ck,hq,wq", [(64, 128, 12, 10), (256, 512, 16, 16), (512, 1024, 8, 6), (32, 64, 10, 12)])
+def test_cla_core_matches_oracle_closed_form(cq, ck, hq, wq):
+    """softmax over image rows, R^2 * a * bilinear(V) (attention.py:208-235)."""
+    from skyeye import engine as E
+    heads, n = 4, 2
+    q = bf16r(randn(("clq", cq, hq), (n, cq, hq, wq)))
+    k = bf16r(randn(("clk", cq, hq), (n, cq, hq // 2, wq // 2)))
+    v = bf16r(randn(("clv", ck, hq), (n, ck, hq // 2, wq // 2)))
+    ku = F.interpolate(k, size=(hq, wq), mode="bilinear", align_corners=False)
+    vu = F.interpolate(v, size=(hq, wq), mode="bilinear", align_corners=False)
+    s = (q.view(n, heads, cq // heads, hq, wq) * ku.view(n, heads, cq // heads, hq, wq)).sum(2) / math.sqrt(cq)
+    a = torch.softmax(s, dim=2)
+    ref = ((4.0 * a).unsqueeze(2) * vu.view(n, heads, ck // heads, hq, wq)).reshape(n, ck, hq, wq)
+    o = E.new_buffer(n, hq, wq, ck)
+    ws = E.workspace(E.N.lib().skb_cla_workspace_bytes(n, hq, wq, heads))
+    E.cla_core(E.from_nchw(q.cuda()), E.from_nchw(k.cuda()), E.from_nchw(v.cuda()), o, heads, 1.0 / math.sqrt(cq), 4.0, ws)
+    torch.cuda.synchronize()
+    assert rel_err(o.nchw(), ref) < TOL
+
+
+@pytest.mark.parametrize("c", [64, 256, 512, 1024])
+def test_layernorm_matches_oracle(c):
+    from skyeye import engine as E
+    x = bf16r(randn(("lnx", c), (2, c, 5, 7), 2.0) + 0.5)
+    g = 1.0 + randn(("lng", c), (c,), 0.1)
+    b = randn(("lnb", c), (c,), 0.1)
+    ref = F.layer_norm(x.permute(0, 2, 3, 1), (c,), g, b, 1e-5).permute(0, 3, 1, 2)  # attention.py:297
+    y = E.new_buffer(2, 5, 7, c)
+    E.layernorm(E.from_nchw(x.cuda()), g.cuda(), b.cuda(), y)
+    torch.cuda.synchronize()
+    assert rel_err(y.nchw(), ref) < TOL
+
+
+def _attn_ref(qkv, heads):
+    B, N, C3 = qkv.shape
+    C = C3 // 3
+    hd = C // heads
+    q, k, v = (z.reshape(B, N, heads, hd).transpose(1, 2) for z in qkv.chunk(3, dim=-1))
+    o = om._attention_chunked(q, k, v, 1.0 / math.sqrt(hd))
+    return o.transpose(1, 2).reshape(B, N, C)
+
+
+@pytest.mark.parametrize("b,h,w,heads", [(1, 16, 16, 1), (2, 16, 24, 2), (1, 4, 4, 4), (2, 10, 10, 1), (1, 40, 40, 4), (1, 64, 80, 2)])
+def test_flash_attention_matches_oracle(b, h, w, heads):
+    """N = h*w tokens incl. ragged query and key tiles (16, 100, 384, 1600, 5120)."""
+    from skyeye import engine as E
+    C = heads * 64
+    qkv = bf16r(randn(("att", b, h, w, heads), (b, h * w, 3 * C)))
+    ref = _attn_ref(qkv, heads)
+    qv = E.View(qkv.view(b, h, w, 3 * C).to(torch.bfloat16).cuda().contiguous())
+    o = E.new_buffer(b, h, w, C)
+    o.t.zero_()
+    E.flash_attn(qv, o, heads, 1.0 / 8.0)
+    torch.cuda.synchronize()
+    got = o.torch().reshape(b, h * w, C).float().cpu()
+    assert rel_err(got, ref) < TOL
+
+
+def test_flash_attention_peaky_logits_exercise_lazy_rescale():
+    """Large-magnitude, position-dependent logits force reference-max growth (O rescale path)."""
+    from skyeye import engine as E
+    b, h, w, heads = 1, 32, 32, 1
+    C = 64
+    qkv = randn(("attp",), (b, h * w, 3 * C))
+    ramp = torch.linspace(0.2, 6.0, h * w).view(1, -1, 1)
+    qkv[..., C:2 * C] *= ramp  # keys grow along the sequence -> running max keeps increasing
+    qkv = bf16r(qkv)
+    ref = _attn_ref(qkv, heads)
+    o = E.new_buffer(b, h, w, C)
+    E.flash_attn(E.View(qkv.view(b, h, w, 3 * C).to(torch.bfloat16).cuda().contiguous()), o, heads, 1.0 / 8.0)
+    torch.cuda.synchronize()
+    assert rel_err(o.torch().reshape(b, h * w, C), ref) < 2e-2
+
+
+@pytest.mark.parametrize("hw", [(64, 96), (160, 128)])
+def test_decode_matches_oracle(hw):
+    """process_detections (detector.py:88-145) incl. the [B,na,h,w,no] relayout of raw outputs."""
+    from skyeye import engine as E
+    H, W = hw
+    B, na, no = 2, 3, 15
+    raws_ref, views = [], []
+    for i, s in enumerate((8, 16, 32)):
+        r = randn(("dec", hw, i), (B, na, H // s, W // s, no), 2.0)
+        raws_ref.append(r)
+        buf = torch.zeros((B, H // s, W // s, 48), dtype=torch.float32, device="cuda")
+        buf[..., :45] = r.permute(0, 2, 3, 1, 4).reshape(B, H // s, W // s, 45).cuda()
+        views.append(E.View(buf))
+    ref = om.decode(raws_ref, (H, W))
+    det = torch.zeros(ref.shape, dtype=torch.float32, device="cuda")
+    raw_out = [torch.zeros(r.shape, dtype=torch.float32, device="cuda") for r in raws_ref]
+    E.decode(views, na, no, om.DEFAULT_ANCHORS, (H, W), det, raw_out)
+    torch.cuda.synchronize()
+    assert rel_err(det, ref) < 1e-5
+    assert float((det.cpu() - ref).abs().max() / ref.abs().clamp_min(1.0).max()) < 1e-5
+    for a, b_ in zip(raw_out, raws_ref):
+        assert torch.equal(a.cpu(), b_)
