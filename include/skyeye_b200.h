@@ -76,6 +76,9 @@ int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const float* bias, 
  * y[n, y, x, p*3 + c] = img[n, c, 2y + dy(p), 2x + dx(p)], patches TL, BL, TR, BR; channels
  * 12..y->c-1 are zero-filled.  img: fp32 [N,3,H,W] contiguous. */
 int skb_focus_nchw_f32(const float* img, int32_t n, int32_t h, int32_t w, const skb_view* y, void* stream);
+/* Same for a uint8 image [N,3,H,W]: the caller's `img.float() / 255` (validate.py:237-238,
+ * detect.py:133-134) is fused into the load, so the host ships 1 byte per sample over PCIe. */
+int skb_focus_nchw_u8(const uint8_t* img, int32_t n, int32_t h, int32_t w, const skb_view* y, void* stream);
 /* nn.MaxPool2d(5, stride 1, pad 2) (blocks.py:143-144); SPP's 9 and 13 pools are cascades of it. */
 int skb_maxpool5_bf16(const skb_view* x, const skb_view* y, void* stream);
 /* CombinedAttention = ChannelAttention + SpatialAttention (attention.py:37-60, 80-98, 118-130).

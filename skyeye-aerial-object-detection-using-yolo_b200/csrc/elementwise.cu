@@ -33,7 +33,13 @@ __device__ __forceinline__ float warp_max(float v) {
 // Focus (blocks.py:170-181): y[n, oy, ox, p*3 + c] = img[n, c, 2*oy + dy(p), 2*ox + dx(p)]
 // patches: p0 TL (0,0), p1 BL (1,0), p2 TR (0,1), p3 BR (1,1); channels >= 12 are zero.
 // ---------------------------------------------------------------------------------------------
-__global__ void focus_kernel(const float* __restrict__ img, int N, int H, int W, __nv_bfloat16* __restrict__ y, int pitch, int cpad) {
+__device__ __forceinline__ float2 focus_ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 focus_ld2(const uint8_t* p) {  // uint8 image: img.float() / 255 (validate.py:237-238)
+    const uchar2 u = *reinterpret_cast<const uchar2*>(p);
+    return make_float2(__fdiv_rn((float)u.x, 255.0f), __fdiv_rn((float)u.y, 255.0f));
+}
+template <typename T>
+__global__ void focus_kernel(const T* __restrict__ img, int N, int H, int W, __nv_bfloat16* __restrict__ y, int pitch, int cpad) {
     const int Ho = H / 2, Wo = W / 2;
     const long total = (long)N * Ho * Wo;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -43,9 +49,9 @@ __global__ void focus_kernel(const float* __restrict__ img, int N, int H, int W,
         float v[12];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float* base = img + (((long)n * 3 + c) * H + 2 * oy) * W + 2 * ox;
-            const float2 top = *reinterpret_cast<const float2*>(base);
-            const float2 bot = *reinterpret_cast<const float2*>(base + W);
+            const T* base = img + (((long)n * 3 + c) * H + 2 * oy) * W + 2 * ox;
+            const float2 top = focus_ld2(base);
+            const float2 bot = focus_ld2(base + W);
             v[0 * 3 + c] = top.x;  // TL
             v[1 * 3 + c] = bot.x;  // BL
             v[2 * 3 + c] = top.y;  // TR
@@ -398,7 +404,19 @@ extern "C" int skb_focus_nchw_f32(const float* img, int32_t n, int32_t h, int32_
     SKB_REQUIRE(h % 2 == 0 && w % 2 == 0 && ((uintptr_t)img & 7) == 0, SKB_ERR_ARG, "focus: H, W must be even (got %dx%d)", h, w);
     SKB_REQUIRE(y->n == n && y->h == h / 2 && y->w == w / 2 && y->c >= 16, SKB_ERR_ARG, "focus: output view mismatch");
     const long total = (long)n * (h / 2) * (w / 2);
-    focus_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, n, h, w, (__nv_bfloat16*)y->ptr, y->pitch, y->c);
+    focus_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, n, h, w, (__nv_bfloat16*)y->ptr, y->pitch, y->c);
+    SKB_LAUNCH_CHECK();
+    return SKB_OK;
+}
+
+extern "C" int skb_focus_nchw_u8(const uint8_t* img, int32_t n, int32_t h, int32_t w, const skb_view* y, void* stream) {
+    int rc = check_device();
+    if (rc != SKB_OK) return rc;
+    SKB_REQUIRE(img && view_ok_bf16(y), SKB_ERR_ARG, "focus_u8: bad arguments");
+    SKB_REQUIRE(h % 2 == 0 && w % 2 == 0 && ((uintptr_t)img & 1) == 0, SKB_ERR_ARG, "focus_u8: H, W must be even (got %dx%d)", h, w);
+    SKB_REQUIRE(y->n == n && y->h == h / 2 && y->w == w / 2 && y->c >= 16, SKB_ERR_ARG, "focus_u8: output view mismatch");
+    const long total = (long)n * (h / 2) * (w / 2);
+    focus_kernel<uint8_t><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, n, h, w, (__nv_bfloat16*)y->ptr, y->pitch, y->c);
     SKB_LAUNCH_CHECK();
     return SKB_OK;
 }

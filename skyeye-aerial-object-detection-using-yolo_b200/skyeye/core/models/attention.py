@@ -54,7 +54,7 @@ class CombinedAttention(nn.Module):
             out = plan.buf(x.n, x.h, x.w, x.c)
         ws = plan.ws(L.E.N.lib().skb_cbam_workspace_bytes(x.n, x.h, x.w, x.c))
         plan.keep += [w0, w1, w7]
-        plan.add(name, lambda s: L.E.cbam(x, w0, w1, w7, out, ws, s))
+        plan.add(name, lambda s: L.E.cbam(x, w0, w1, w7, out, ws, s), "cbam", 0.0, 2.0 * x.n * x.h * x.w * x.c * 4, 4)
         return out
 
     def forward(self, x):
@@ -87,7 +87,9 @@ class CrossLayerAttention(nn.Module):
         ws = plan.ws(L.E.N.lib().skb_cla_workspace_bytes(query.n, query.h, query.w, self.heads))
         k, v = kv.slice(0, cq), kv.slice(cq, cq + cv)
         r2 = float(self.region_size * self.region_size)
-        plan.add(name + ".core", lambda s: L.E.cla_core(q, k, v, o, self.heads, self.scale, r2, ws, s))
+        npx = query.n * query.h * query.w
+        plan.add(name + ".core", lambda s: L.E.cla_core(q, k, v, o, self.heads, self.scale, r2, ws, s), "cla", 0.0,
+                 2.0 * npx * (cq + cv) + 2.0 * (npx // 4) * (cq + cv), 3)
         if out is None:
             out = plan.buf(query.n, query.h, query.w, self.output_projection.out_channels)
         po = PackedConv(self.output_projection.weight, self.output_projection.bias, dev)
@@ -122,16 +124,18 @@ class TransformerLayer(nn.Module):
         plan.keep += [g1, b1, g2, b2]
         n, h, w = x.n, x.h, x.w
         xn = plan.buf(n, h, w, C)
-        plan.add(name + ".ln1", lambda s: L.E.layernorm(x, g1, b1, xn, self.norm1.eps, s))
+        plan.add(name + ".ln1", lambda s: L.E.layernorm(x, g1, b1, xn, self.norm1.eps, s), "layernorm", 0.0, 4.0 * n * h * w * C)
         qkv = plan.buf(n, h, w, 3 * C)
         plan.conv(name + ".qkv", xn, PackedConv(self.self_attn.in_proj_weight, self.self_attn.in_proj_bias, dev), qkv, 1, ACT_NONE)
         o = plan.buf(n, h, w, C)
         scale = 1.0 / math.sqrt(C // self.num_heads)
-        plan.add(name + ".attn", lambda s: L.E.flash_attn(qkv, o, self.num_heads, scale, s))
+        ntok = h * w
+        plan.add(name + ".attn", lambda s: L.E.flash_attn(qkv, o, self.num_heads, scale, s), "attention",
+                 4.0 * n * float(ntok) * ntok * C, 2.0 * n * ntok * 4 * C)  # 4*N^2*C per image
         t = plan.buf(n, h, w, C)
         plan.conv(name + ".proj", o, PackedConv(self.self_attn.out_proj.weight, self.self_attn.out_proj.bias, dev), t, 1, ACT_NONE, x)
         xn2 = plan.buf(n, h, w, C)
-        plan.add(name + ".ln2", lambda s: L.E.layernorm(t, g2, b2, xn2, self.norm2.eps, s))
+        plan.add(name + ".ln2", lambda s: L.E.layernorm(t, g2, b2, xn2, self.norm2.eps, s), "layernorm", 0.0, 4.0 * n * h * w * C)
         ff0, ff3 = self.feedforward[0], self.feedforward[3]
         hid = plan.buf(n, h, w, ff0.out_features)
         plan.conv(name + ".ff0", xn2, PackedConv(ff0.weight, ff0.bias, dev), hid, 1, ACT_RELU)

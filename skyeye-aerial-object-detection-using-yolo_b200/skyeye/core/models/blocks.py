@@ -105,7 +105,7 @@ class SPPBlock(nn.Module):
         self.cv1.lower(plan, x, cat.slice(0, h), name=name + ".cv1")
         for i in range(3):  # mp9 = mp5(mp5), mp13 = mp5(mp5(mp5)) with -inf padding: exact
             src, dst = cat.slice(i * h, (i + 1) * h), cat.slice((i + 1) * h, (i + 2) * h)
-            plan.add(f"{name}.mp{5 + 4 * i}", lambda s, a=src, b=dst: L.E.maxpool5(a, b, s))
+            plan.add(f"{name}.mp{5 + 4 * i}", lambda s, a=src, b=dst: L.E.maxpool5(a, b, s), "maxpool", 0.0, 4.0 * x.n * x.h * x.w * h)
         return self.cv2.lower(plan, cat, out, name=name + ".cv2")
 
     def forward(self, x):
@@ -126,5 +126,5 @@ class FocusBlock(nn.Module):
     def lower_image(self, plan: Plan, img_holder, n, h, w, name="focus") -> View:
         cpad = 64 if self.conv.out_channels % 64 == 0 else 32
         f = plan.buf(n, h // 2, w // 2, cpad)
-        plan.add(name + ".s2d", lambda s: L.E.focus(img_holder[0], f, s))
+        plan.add(name + ".s2d", lambda s: L.E.focus(img_holder[0], f, s), "focus", 0.0, 3.0 * n * h * w * 4 + 2.0 * n * (h // 2) * (w // 2) * cpad)
         return self.conv.lower(plan, f, name=name + ".conv")

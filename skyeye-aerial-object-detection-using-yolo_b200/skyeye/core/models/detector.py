@@ -58,7 +58,8 @@ class DetectionHead(nn.Module):
         det = torch.empty((raws[0].n, rows, no), dtype=torch.float32, device=plan.device)
         raw_out = [torch.empty((r.n, na, r.h, r.w, no), dtype=torch.float32, device=plan.device) for r in raws]
         plan.keep += [det, raw_out]
-        plan.add("decode", lambda s: E.decode(raws, na, no, self.anchors, input_hw, det, raw_out, s))
+        plan.add("decode", lambda s: E.decode(raws, na, no, self.anchors, input_hw, det, raw_out, s), "decode", 0.0,
+                 4.0 * raws[0].n * rows * no * 3)
         return det, raw_out
 
 
@@ -167,6 +168,7 @@ class SkyEyeDetector(nn.Module):
                                        self.cfg.get("width_multiple", 1.0))
         self.neck = FeatureNeck(self.backbone.channels, self.cfg.get("width_multiple", 1.0))
         self.detection_head = DetectionHead(self.cfg["nc"], self.cfg.get("anchors"), self.neck.out_channels)
+        self._initialize_weights()
         self.stride = torch.tensor([8, 16, 32])
         self.names = [str(i) for i in range(self.cfg["nc"])]
         self._plans = {}
@@ -180,6 +182,22 @@ class SkyEyeDetector(nn.Module):
             self.to(device)
 
     # -- weights ---------------------------------------------------------------------------------
+    def _initialize_weights(self):
+        """Random init with the reference's distributions (detector.py:326-341, with the bias guard R1)."""
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+                nn.init.normal_(m.weight, 0.0, (2.0 / n) ** 0.5)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, 0.0, 0.01)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+
     def load_from_pretrained(self, weights_path):
         """Checkpoint formats of detector.py:353-359: {'model': nn.Module}, {'state_dict': ...} or a bare
         state dict; keys filtered by name + shape, strict=False."""
@@ -231,7 +249,8 @@ class SkyEyeDetector(nn.Module):
             raise NotImplementedError("training is outside the B200 forward-path scope (SURVEY.md §2)")
         if not x.is_cuda:
             raise RuntimeError("SkyEyeDetector (B200) needs a CUDA tensor; there is no CPU fallback")
-        xin = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
+        # fp32 images in [0,1] as in the reference; uint8 images are scaled by 1/255 inside the first kernel
+        xin = x if (x.dtype in (torch.float32, torch.uint8) and x.is_contiguous()) else x.float().contiguous()
         plan = self.plan_for(xin)
         if self.use_cuda_graph:
             if plan.graph is None:
@@ -272,6 +291,7 @@ class EnhancedSkyEyeDetector(SkyEyeDetector):
             self.head_transformers = nn.ModuleList(TransformerLayer(c, max(c // hd, 1)) for c in (c3, c4, c5))
         else:
             self.head_transformers = None
+        self._initialize_weights()
         self.eval()
         if weights is not None:
             self.load_from_pretrained(weights)

@@ -128,9 +128,10 @@ def conv2d(x: View, pw: PackedConv, y: View, stride: int = 1, act: int = ACT_SIL
 
 
 def focus(img: torch.Tensor, y: View, stream=None) -> None:
-    assert img.dtype == torch.float32 and img.is_contiguous() and img.dim() == 4 and img.shape[1] == 3
+    assert img.dtype in (torch.float32, torch.uint8) and img.is_contiguous() and img.dim() == 4 and img.shape[1] == 3
     n, _, h, w = img.shape
-    N.check(N.lib().skb_focus_nchw_f32(img.data_ptr(), n, h, w, y.ref, _stream_ptr() if stream is None else stream), "skb_focus_nchw_f32")
+    fn = N.lib().skb_focus_nchw_f32 if img.dtype == torch.float32 else N.lib().skb_focus_nchw_u8
+    N.check(fn(img.data_ptr(), n, h, w, y.ref, _stream_ptr() if stream is None else stream), "skb_focus_nchw")
 
 
 def maxpool5(x: View, y: View, stream=None) -> None:
@@ -184,6 +185,7 @@ class Plan:
         self.device = device
         self.steps: List[Callable[[int], None]] = []
         self.names: List[str] = []
+        self.meta: List[dict] = []  # per step: kind, algorithmic flops / bytes, kernel launches
         self.keep = []  # buffers / packed weights kept alive
         self.graph = None
         self.n_launch_calls = 0
@@ -198,14 +200,22 @@ class Plan:
         self.keep.append(t)
         return t
 
-    def add(self, name: str, fn: Callable[[int], None]) -> None:
+    def add(self, name: str, fn: Callable[[int], None], kind: str = "other", flops: float = 0.0, bytes: float = 0.0,
+            launches: int = 1) -> None:
         self.names.append(name)
         self.steps.append(fn)
+        self.meta.append(dict(kind=kind, flops=float(flops), bytes=float(bytes), launches=int(launches)))
 
     # -- op builders ---------------------------------------------------------------------------
     def conv(self, name, x: View, pw: PackedConv, y: View, stride=1, act=ACT_SILU, residual=None, upsample2x=False):
         self.keep.append(pw)
-        self.add(name, lambda s: conv2d(x, pw, y, stride, act, residual, upsample2x, s))
+        ho, wo = x.h // stride, x.w // stride
+        m = x.n * ho * wo
+        flops = 2.0 * m * pw.cout * pw.k * pw.k * x.c  # algorithmic 2*M*N*K
+        esz = 4 if y.dtype == SKB_F32 else 2
+        nbytes = 2.0 * x.n * x.h * x.w * x.c + 2.0 * pw.w.numel() + esz * m * y.c * (4 if upsample2x else 1) + \
+            (2.0 * m * y.c if residual is not None else 0.0)
+        self.add(name, lambda s: conv2d(x, pw, y, stride, act, residual, upsample2x, s), "conv", flops, nbytes, 1)
         return y
 
     def run(self, stream: Optional[int] = None) -> None:
@@ -213,8 +223,12 @@ class Plan:
         for fn in self.steps:
             fn(s)
 
+    @property
+    def launches(self) -> int:
+        return sum(m["launches"] for m in self.meta)
+
     def run_timed(self):
-        """Per-step CUDA-event timing (profiling aid): list of (name, ms)."""
+        """Per-step CUDA-event timing on the launching stream: list of (name, ms)."""
         evs = []
         s = _stream_ptr()
         for fn in self.steps:
