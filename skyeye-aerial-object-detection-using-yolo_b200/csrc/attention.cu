@@ -151,17 +151,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty(sb));
-            // scaled scores (log2 domain), mask keys beyond N on the ragged last tile
+            // row max of the raw scores (keys beyond N masked on the ragged last tile)
             float mx = -INFINITY;
             const int kbase = j * ATT_BKV;
-            const bool ragged = kbase + ATT_BKV > p.N;
+            if (kbase + ATT_BKV > p.N) {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) {
-                float v = __uint_as_float(sv[i]) * p.scale_log2;
-                if (ragged && kbase + i >= p.N) v = -INFINITY;
-                sv[i] = __float_as_uint(v);
-                mx = fmaxf(mx, v);
+                for (int i = 0; i < 64; ++i)
+                    if (kbase + i >= p.N) sv[i] = 0xff800000u;  // -inf
             }
+#pragma unroll
+            for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+            mx *= p.scale_log2;  // log2 domain (scale > 0)
             // lazy reference max: rescale only if some row's max grew by more than 8 (p stays <= 2^8)
             const bool need = mx > m_ref + 8.0f;
             const bool any = __any_sync(0xffffffffu, need);
@@ -190,7 +190,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 float e[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    e[i] = exp2f(__uint_as_float(sv[c * 8 + i]) - m_ref);
+                    e[i] = ex2_approx(fmaf(__uint_as_float(sv[c * 8 + i]), p.scale_log2, -m_ref));  // one FFMA + one MUFU
                     sum += e[i];
                 }
                 uint4 u;

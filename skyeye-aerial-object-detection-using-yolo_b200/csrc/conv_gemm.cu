@@ -11,9 +11,13 @@
 // * B operand: weights [Cout_pad][taps*Cin] bf16 (BN folded), 2-D tensor map, same swizzle.
 // * Accumulators: fp32 in TMEM, double buffered (2 x BN columns) so the epilogue of tile i overlaps
 //   the MMAs of tile i+1.  Persistent CTAs, static tile schedule (Cout block fastest).
-// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue
-//   (tcgen05.ld -> +bias -> SiLU/ReLU -> +residual -> bf16/fp32 store into a channel slice of the
-//   destination buffer; optional 2x2 replication = fused nearest upsample).
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue:
+//   tcgen05.ld -> +bias (staged in smem) -> SiLU/ReLU -> +residual -> bf16/fp32, written into a ring
+//   of 16 KB swizzled smem sub-tiles (64 bf16 / 32 fp32 channels x 128 pixels) that one elected
+//   thread drains with TMA stores (coalesced, asynchronous, edge clipping for free) into a channel
+//   slice of the destination buffer.  The residual sub-tile is TMA-prefetched into the same ring
+//   slot one sub-tile ahead and updated in place.  (The two 2x-upsampling lateral convs keep a
+//   direct replicated-store epilogue.)
 //
 // Replaces ConvolutionBlock.forward (skyeye/core/models/blocks.py:36-38) and friends, see
 // include/skyeye_b200.h.
@@ -36,6 +40,7 @@ struct ConvParams {
     long long res_pitch;
     const float* bias;
     int act;
+    int has_res, sub_cols, epi_box_bytes;
 };
 
 template <int BN, int BK>
@@ -43,14 +48,20 @@ struct ConvCfg {
     static constexpr int A_BYTES = 128 * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (196608 / STAGE_BYTES) < 8 ? (196608 / STAGE_BYTES) : 8;
+    static constexpr int EPI_NB = 3;           // epilogue staging ring (sub-tiles)
+    static constexpr int EPI_BUF = 16384;      // 128 rows x 128 B
+    static constexpr int EPI_BYTES = EPI_NB * EPI_BUF + BN * 4;
+    static constexpr int MAIN_BUDGET = 227 * 1024 - 1024 - 512 - EPI_BYTES;
+    static constexpr int STAGES = (MAIN_BUDGET / STAGE_BYTES) < 8 ? (MAIN_BUDGET / STAGE_BYTES) : 8;
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // 64..512, power of two
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 512;
+    static constexpr int SUBC_BF16 = BN >= 64 ? 64 : 32;
 };
 
 template <int BN, int BK>
 __global__ void __launch_bounds__(192, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const ConvParams p) {
     using Cfg = ConvCfg<BN, BK>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr uint32_t SW = BK == 64 ? UMMA_SW128 : UMMA_SW64;
@@ -61,12 +72,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t base = (raw + 1023u) & ~1023u;
     const uint32_t sA0 = base;
     const uint32_t sB0 = base + STAGES * Cfg::A_BYTES;
-    const uint32_t bar0 = base + STAGES * Cfg::STAGE_BYTES;
+    const uint32_t ebuf0 = base + STAGES * Cfg::STAGE_BYTES;
+    const uint32_t sbias = ebuf0 + Cfg::EPI_NB * Cfg::EPI_BUF;
+    const uint32_t bar0 = sbias + BN * 4;
     auto full = [&](int s) { return bar0 + 8u * s; };
     auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
     auto tfull = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
     auto tempty = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
-    const uint32_t slot = bar0 + 8u * (2 * STAGES + 4);
+    auto res_full = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + s); };
+    const uint32_t slot = bar0 + 8u * (2 * STAGES + 4 + Cfg::EPI_NB);
     volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -74,6 +88,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmY);
+        if (p.has_res) tma_prefetch_desc(&tmR);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -85,6 +101,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_init(tfull(s), 1);
                 mbar_init(tempty(s), 4);
             }
+            for (int s = 0; s < Cfg::EPI_NB; ++s) mbar_init(res_full(s), 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -155,14 +172,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else {
         // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+        constexpr int NB = Cfg::EPI_NB;
         const int q = warp & 3;
-        const int m = q * 32 + lane;
+        const int m = q * 32 + lane;              // accumulator row = pixel of the tile = TMEM lane
+        const int te = (int)threadIdx.x - 64;     // 0..127 within the epilogue group
+        const bool T0 = te == 0;                  // issues the TMA stores / residual prefetches
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const int hw = p.th * p.tw;
         const int nl = m / hw;
         const int rem = m - nl * hw;
         const int hl = rem / p.tw;
         const int wl = rem - hl * p.tw;
         const bool row_in_box = m < p.tn * hw;
+        const int sub_cols = p.sub_cols;
+        const uint32_t row_bytes = (uint32_t)sub_cols * (p.out_f32 ? 4u : 2u);
+        const uint32_t sw = row_bytes == 128 ? (uint32_t)(m & 7) : 0u;  // SWIZZLE_128B: 16 B chunk ^= row % 8
+        const uint32_t row_off = (uint32_t)m * row_bytes;
+        uint32_t qseq = 0;  // running sub-tile number: ring slot = qseq % NB
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -172,76 +198,168 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mt /= p.tiles_w;
             const int ih = mt % p.tiles_h;
             const int in = mt / p.tiles_h;
-            const int n = in * p.tn + nl, h = ih * p.th + hl, w = iw * p.tw + wl;
-            const bool valid = row_in_box && n < p.B && h < p.Ho && w < p.Wo;
-            const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
-            const size_t opix = p.up2 ? (((size_t)n * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) : pix;
+            const int w0 = iw * p.tw, h0 = ih * p.th, n0 = in * p.tn;
+            const int ncol0 = nb * BN;
+            const uint32_t acc = tmem_base + lane_addr + (uint32_t)(as * BN);
 
-            mbar_wait(tfull(as), aphase);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
-                tmem_ld_wait();
-                if (c0 + 32 >= BN) {  // accumulator fully drained into registers: hand TMEM back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty(as));
+            if (!p.up2) {
+                // ------------- smem-staged epilogue drained by TMA stores -------------
+                int nvalid = (p.cout - ncol0 + sub_cols - 1) / sub_cols;
+                nvalid = nvalid < 0 ? 0 : (nvalid > BN / sub_cols ? BN / sub_cols : nvalid);
+                for (int i = te; i < BN; i += 128) sts32f(sbias + 4u * i, __ldg(p.bias + ncol0 + i));
+                if (T0 && nvalid > 0) {
+                    tma_store_wait_read<NB - 1>();  // ring slot of the first sub-tile is drained
+                    if (p.has_res) {
+                        mbar_expect_tx(res_full(qseq % NB), (uint32_t)p.epi_box_bytes);
+                        tma_load_4d(ebuf0 + (qseq % NB) * Cfg::EPI_BUF, &tmR, res_full(qseq % NB), ncol0, w0, h0, n0);
+                    }
                 }
-                const int ncol = nb * BN + c0;
-                if (valid) {
+                __syncwarp();
+                named_bar_sync(1, 128);  // bias visible, slot free
+                mbar_wait(tfull(as), aphase);
+                tc_fence_after();
+                for (int sub = 0; sub < nvalid; ++sub, ++qseq) {
+                    const uint32_t slot_i = qseq % NB;
+                    const uint32_t buf = ebuf0 + slot_i * Cfg::EPI_BUF;
+                    const int c0 = sub * sub_cols;
+                    if (T0) {
+                        tma_store_wait_read<NB - 2>();  // slot of the NEXT sub-tile is drained
+                        if (p.has_res && sub + 1 < nvalid) {
+                            const uint32_t s2 = (qseq + 1) % NB;
+                            mbar_expect_tx(res_full(s2), (uint32_t)p.epi_box_bytes);
+                            tma_load_4d(ebuf0 + s2 * Cfg::EPI_BUF, &tmR, res_full(s2), ncol0 + c0 + sub_cols, w0, h0, n0);
+                        }
+                    }
+                    __syncwarp();
+                    uint32_t v[64];
+                    {
+                        uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+                        tmem_ld32(acc + (uint32_t)c0, lo);
+                        if (sub_cols == 64) {
+                            uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+                            tmem_ld32(acc + (uint32_t)c0 + 32, hi);
+                        }
+                    }
+                    tmem_ld_wait();
+                    if (sub == nvalid - 1) {  // accumulator fully drained into registers: hand TMEM back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty(as));
+                    }
+                    if (p.has_res) mbar_wait(res_full(slot_i), (qseq / NB) & 1u);
+                    const uint32_t rowp = buf + row_off;
+                    if (!p.out_f32) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int col = ncol + g * 8;
-                        if (col < p.cout) {
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+                        for (int j = 0; j < Cfg::SUBC_BF16 / 8; ++j) {
                             float f[8];
-                            f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
-                            f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
-                            f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
-                            f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
-                            f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x;
-                            f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
-                            f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
-                            f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j * 8 + i]) + lds32f(sbias + 4u * (c0 + j * 8 + i));
                             if (p.act == SKB_ACT_SILU) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+                                for (int i = 0; i < 8; ++i) f[i] = silu_f(f[i]);
                             } else if (p.act == SKB_ACT_RELU) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
+                                for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);
                             }
-                            if (p.res) {
-                                const uint4 r = *reinterpret_cast<const uint4*>(p.res + pix * p.res_pitch + col);
+                            const uint32_t a16 = rowp + (((uint32_t)j ^ sw) << 4);
+                            if (p.has_res) {
+                                const uint4 r = lds128(a16);
                                 f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
                                 f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
                                 f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
                                 f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
                             }
-                            if (p.out_f32) {
-                                float* o = reinterpret_cast<float*>(p.out) + opix * p.out_pitch + col;
-                                const float4 o0 = make_float4(f[0], f[1], f[2], f[3]);
-                                const float4 o1 = make_float4(f[4], f[5], f[6], f[7]);
-                                *reinterpret_cast<float4*>(o) = o0;
-                                *reinterpret_cast<float4*>(o + 4) = o1;
-                                if (p.up2) {
-                                    const size_t dx = (size_t)p.out_pitch, dy = (size_t)(2 * p.Wo) * p.out_pitch;
+                            uint4 o4;
+                            o4.x = pack_bf16x2(f[0], f[1]);
+                            o4.y = pack_bf16x2(f[2], f[3]);
+                            o4.z = pack_bf16x2(f[4], f[5]);
+                            o4.w = pack_bf16x2(f[6], f[7]);
+                            sts128(a16, o4);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float f[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) f[i] = __uint_as_float(v[j * 4 + i]) + lds32f(sbias + 4u * (c0 + j * 4 + i));
+                            if (p.act == SKB_ACT_SILU) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) f[i] = silu_f(f[i]);
+                            } else if (p.act == SKB_ACT_RELU) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) f[i] = fmaxf(f[i], 0.0f);
+                            }
+                            uint4 o4;
+                            o4.x = __float_as_uint(f[0]); o4.y = __float_as_uint(f[1]);
+                            o4.z = __float_as_uint(f[2]); o4.w = __float_as_uint(f[3]);
+                            sts128(rowp + (((uint32_t)j ^ sw) << 4), o4);
+                        }
+                    }
+                    fence_proxy_async_smem();    // generic-proxy smem writes -> visible to the TMA engine
+                    named_bar_sync(1, 128);
+                    if (T0) {
+                        tma_store_4d(&tmY, buf, ncol0 + c0, w0, h0, n0);
+                        tma_store_commit();
+                    }
+                    __syncwarp();
+                }
+                if (nvalid == 0) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty(as));
+                }
+            } else {
+                // ------------- direct replicated stores (2x nearest upsample fused) -------------
+                const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
+                const bool valid = row_in_box && n < p.B && h < p.Ho && w < p.Wo;
+                const size_t opix = ((size_t)n * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w;
+                mbar_wait(tfull(as), aphase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(acc + (uint32_t)c0, v);
+                    tmem_ld_wait();
+                    if (c0 + 32 >= BN) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty(as));
+                    }
+                    const int ncol = ncol0 + c0;
+                    if (valid) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const int col = ncol + g * 8;
+                            if (col < p.cout) {
+                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+                                float f[8];
+                                f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+                                f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+                                f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+                                f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+                                if (p.act == SKB_ACT_SILU) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+                                } else if (p.act == SKB_ACT_RELU) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
+                                }
+                                const size_t dx = (size_t)p.out_pitch, dy = (size_t)(2 * p.Wo) * p.out_pitch;
+                                if (p.out_f32) {
+                                    float* o = reinterpret_cast<float*>(p.out) + opix * p.out_pitch + col;
+                                    const float4 o0 = make_float4(f[0], f[1], f[2], f[3]);
+                                    const float4 o1 = make_float4(f[4], f[5], f[6], f[7]);
+                                    *reinterpret_cast<float4*>(o) = o0; *reinterpret_cast<float4*>(o + 4) = o1;
                                     *reinterpret_cast<float4*>(o + dx) = o0; *reinterpret_cast<float4*>(o + dx + 4) = o1;
                                     *reinterpret_cast<float4*>(o + dy) = o0; *reinterpret_cast<float4*>(o + dy + 4) = o1;
                                     *reinterpret_cast<float4*>(o + dy + dx) = o0; *reinterpret_cast<float4*>(o + dy + dx + 4) = o1;
-                                }
-                            } else {
-                                uint4 o4;
-                                o4.x = pack_bf16x2(f[0], f[1]);
-                                o4.y = pack_bf16x2(f[2], f[3]);
-                                o4.z = pack_bf16x2(f[4], f[5]);
-                                o4.w = pack_bf16x2(f[6], f[7]);
-                                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_pitch + col;
-                                *reinterpret_cast<uint4*>(o) = o4;
-                                if (p.up2) {
-                                    const size_t dx = (size_t)p.out_pitch, dy = (size_t)(2 * p.Wo) * p.out_pitch;
+                                } else {
+                                    uint4 o4;
+                                    o4.x = pack_bf16x2(f[0], f[1]); o4.y = pack_bf16x2(f[2], f[3]);
+                                    o4.z = pack_bf16x2(f[4], f[5]); o4.w = pack_bf16x2(f[6], f[7]);
+                                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_pitch + col;
+                                    *reinterpret_cast<uint4*>(o) = o4;
                                     *reinterpret_cast<uint4*>(o + dx) = o4;
                                     *reinterpret_cast<uint4*>(o + dy) = o4;
                                     *reinterpret_cast<uint4*>(o + dy + dx) = o4;
@@ -254,6 +372,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             as ^= 1;
             if (as == 0) aphase ^= 1;
         }
+        if (T0) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -265,7 +384,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // host side
 // ---------------------------------------------------------------------------------------------
 template <int BN, int BK>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR, ConvParams p,
+                       cudaStream_t stream) {
     using Cfg = ConvCfg<BN, BK>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -273,7 +393,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
         attr_set = true;
     }
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    conv_gemm_kernel<BN, BK><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    conv_gemm_kernel<BN, BK><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, p);
     SKB_LAUNCH_CHECK();
     return SKB_OK;
 }
@@ -379,8 +499,12 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
     p.res = residual ? (const __nv_bfloat16*)residual->ptr : nullptr;
     p.res_pitch = residual ? residual->pitch : 0;
     p.bias = bias; p.act = act;
+    p.has_res = residual ? 1 : 0;
+    if (residual) SKB_REQUIRE(y->dtype == SKB_BF16, SKB_ERR_UNSUPPORTED, "conv2d: residual needs a bf16 output");
+    p.sub_cols = p.out_f32 ? 32 : (BN >= 64 ? 64 : 32);
+    p.epi_box_bytes = p.tn * p.th * p.tw * 128;
 
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmY, tmR;
     {
         const uint64_t pitchB = (uint64_t)x->pitch * 2;
         uint64_t dims[5], str[4];
@@ -399,10 +523,32 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
         uint32_t bb[2] = {(uint32_t)BK, (uint32_t)BN};
         rc = encode_tensor_map(&tmB, w_packed, 2, 2, bd, bs, bb, BK * 2);
         if (rc != SKB_OK) return rc;
+        // epilogue maps: 4-D {c, w, h, n} boxes of sub_cols channels x (tw, th, tn) pixels, 128-byte rows
+        const int esz = p.out_f32 ? 4 : 2;
+        const int row_bytes = p.sub_cols * esz;
+        uint64_t yd[4] = {(uint64_t)y->c, (uint64_t)y->w, (uint64_t)y->h, (uint64_t)y->n};
+        uint64_t ys[3] = {(uint64_t)y->pitch * esz, (uint64_t)y->pitch * esz * y->w, (uint64_t)y->pitch * esz * y->w * y->h};
+        uint32_t yb[4] = {(uint32_t)p.sub_cols, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
+        if (!upsample2x) {
+            rc = encode_tensor_map(&tmY, y->ptr, esz, 4, yd, ys, yb, row_bytes == 128 ? 128 : 0);
+            if (rc != SKB_OK) return rc;
+        } else {
+            tmY = tmB;  // unused by the direct-store epilogue
+        }
+        if (residual) {
+            uint64_t rd[4] = {(uint64_t)residual->c, (uint64_t)residual->w, (uint64_t)residual->h, (uint64_t)residual->n};
+            uint64_t rs[3] = {(uint64_t)residual->pitch * 2, (uint64_t)residual->pitch * 2 * residual->w,
+                              (uint64_t)residual->pitch * 2 * residual->w * residual->h};
+            rc = encode_tensor_map(&tmR, residual->ptr, 2, 4, rd, rs, yb, row_bytes == 128 ? 128 : 0);
+            if (rc != SKB_OK) return rc;
+            p.epi_box_bytes = p.tn * p.th * p.tw * row_bytes;
+        } else {
+            tmR = tmB;
+        }
     }
     cudaStream_t st = (cudaStream_t)stream;
 #define SKB_CONV_CASE(bn, bk) \
-    if (BN == bn && BK == bk) return launch_conv<bn, bk>(tmA, tmB, p, st);
+    if (BN == bn && BK == bk) return launch_conv<bn, bk>(tmA, tmB, tmY, tmR, p, st);
     SKB_CONV_CASE(256, 64) SKB_CONV_CASE(128, 64) SKB_CONV_CASE(64, 64) SKB_CONV_CASE(32, 64)
     SKB_CONV_CASE(256, 32) SKB_CONV_CASE(128, 32) SKB_CONV_CASE(64, 32) SKB_CONV_CASE(32, 32)
 #undef SKB_CONV_CASE

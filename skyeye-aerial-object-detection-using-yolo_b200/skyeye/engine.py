@@ -81,6 +81,7 @@ class PackedConv:
         assert kh == kw
         cin_p = cin if cin_pad is None else cin_pad
         self.cout, self.cin, self.k = cout, cin_p, kh
+        self.cin_real = cin
         self.cout_pad = round_cout(cout)
         wp = torch.zeros((self.cout_pad, kh, kw, cin_p), dtype=torch.float32)
         wp[:cout, :, :, :cin] = w.permute(0, 2, 3, 1).cpu()
@@ -104,6 +105,7 @@ class PackedConv:
             "only the last part of a fused conv may have padded output channels"
         out = PackedConv.__new__(PackedConv)
         out.cin, out.k = p0.cin, p0.k
+        out.cin_real = p0.cin_real
         out.cout = sum(p.cout for p in parts)
         w = torch.cat([p.w[:p.cout] for p in parts], 0)
         b = torch.cat([p.b[:p.cout] for p in parts], 0)
@@ -211,7 +213,7 @@ class Plan:
         self.keep.append(pw)
         ho, wo = x.h // stride, x.w // stride
         m = x.n * ho * wo
-        flops = 2.0 * m * pw.cout * pw.k * pw.k * x.c  # algorithmic 2*M*N*K
+        flops = 2.0 * m * pw.cout * pw.k * pw.k * pw.cin_real  # algorithmic 2*M*N*K, unpadded
         esz = 4 if y.dtype == SKB_F32 else 2
         nbytes = 2.0 * x.n * x.h * x.w * x.c + 2.0 * pw.w.numel() + esz * m * y.c * (4 if upsample2x else 1) + \
             (2.0 * m * y.c if residual is not None else 0.0)
