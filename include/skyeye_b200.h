@@ -71,6 +71,10 @@ int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const float* bias, 
                     const skb_view* y, int32_t cout_pad, int32_t ksize, int32_t stride, int32_t act,
                     int32_t upsample2x, void* stream);
 
+/* Debug aid, not part of the drop-in surface: CTA 0 of every following conv launch records
+ * (event, clock64) pairs into this device buffer of 3*8192 int64; NULL switches tracing off. */
+int skb_debug_conv_trace(void* device_buffer);
+
 /* ---- layout / pooling / attention-gate kernels (HBM-bound) ------------------------------------ */
 /* FocusBlock space-to-depth (blocks.py:170-181) fused with the NCHW fp32 -> NHWC bf16 conversion:
  * y[n, y, x, p*3 + c] = img[n, c, 2y + dy(p), 2x + dx(p)], patches TL, BL, TR, BR; channels

@@ -159,8 +159,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 for (int i = 0; i < 64; ++i)
                     if (kbase + i >= p.N) sv[i] = 0xff800000u;  // -inf
             }
+            {   // 8 independent chains instead of one 64-deep dependent FMNMX chain
+                float m8[8];
 #pragma unroll
-            for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+                for (int i = 0; i < 8; ++i) m8[i] = __uint_as_float(sv[i]);
+#pragma unroll
+                for (int i = 8; i < 64; ++i) m8[i & 7] = fmaxf(m8[i & 7], __uint_as_float(sv[i]));
+                mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+            }
             mx *= p.scale_log2;  // log2 domain (scale > 0)
             // lazy reference max: rescale only if some row's max grew by more than 8 (p stays <= 2^8)
             const bool need = mx > m_ref + 8.0f;
@@ -183,7 +189,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 tmem_st_wait();
             }
             m_ref = m_new;
-            float sum = 0.f;
+            float sum8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             uint8_t* prow = sP_ptr + row * 128;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -191,14 +197,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     e[i] = ex2_approx(fmaf(__uint_as_float(sv[c * 8 + i]), p.scale_log2, -m_ref));  // one FFMA + one MUFU
-                    sum += e[i];
+                    sum8[i] += e[i];
                 }
                 uint4 u;
                 u.x = pack_bf16x2(e[0], e[1]); u.y = pack_bf16x2(e[2], e[3]);
                 u.z = pack_bf16x2(e[4], e[5]); u.w = pack_bf16x2(e[6], e[7]);
                 *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = u;  // SWIZZLE_128B: 16B chunk ^= row % 8
             }
-            l += sum;
+            l += ((sum8[0] + sum8[1]) + (sum8[2] + sum8[3])) + ((sum8[4] + sum8[5]) + (sum8[6] + sum8[7]));
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();

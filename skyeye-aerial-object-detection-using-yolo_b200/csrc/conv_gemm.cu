@@ -11,7 +11,9 @@
 // * B operand: weights [Cout_pad][taps*Cin] bf16 (BN folded), 2-D tensor map, same swizzle.
 // * Accumulators: fp32 in TMEM, double buffered (2 x BN columns) so the epilogue of tile i overlaps
 //   the MMAs of tile i+1.  Persistent CTAs, static tile schedule (Cout block fastest).
-// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue:
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue
+//   (two warps per TMEM lane quarter, each taking half of the sub-tile's columns, so every SM
+//   sub-partition has two epilogue warps to overlap MUFU / smem / TMEM latencies):
 //   tcgen05.ld -> +bias (staged in smem) -> SiLU/ReLU -> +residual -> bf16/fp32, written into a ring
 //   of 16 KB swizzled smem sub-tiles (64 bf16 / 32 fp32 channels x 128 pixels) that one elected
 //   thread drains with TMA stores (coalesced, asynchronous, edge clipping for free) into a channel
@@ -41,7 +43,14 @@ struct ConvParams {
     const float* bias;
     int act;
     int has_res, sub_cols, epi_box_bytes;
+    long long* trace;  // debug timeline of CTA 0 (null = off): [role][event] = clock64
 };
+
+// debug timeline: role 0 = producer, 1 = MMA, 2 = epilogue warp 2 lane 0; 4096 events per role
+#define SKB_TR(role, ev)                                                                         \
+    do {                                                                                         \
+        if (p.trace && blockIdx.x == 0 && tr_n < 4096) { p.trace[(role) * 8192 + 2 * tr_n] = (ev); p.trace[(role) * 8192 + 2 * tr_n + 1] = clock64(); ++tr_n; } \
+    } while (0)
 
 template <int BN, int BK>
 struct ConvCfg {
@@ -59,7 +68,7 @@ struct ConvCfg {
 };
 
 template <int BN, int BK>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const ConvParams p) {
     using Cfg = ConvCfg<BN, BK>;
@@ -99,7 +108,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(tfull(s), 1);
-                mbar_init(tempty(s), 4);
+                mbar_init(tempty(s), 8);
             }
             for (int s = 0; s < Cfg::EPI_NB; ++s) mbar_init(res_full(s), 1);
             fence_barrier_init();
@@ -117,6 +126,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            int tr_n = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int nb = tile % p.n_blocks;
                 int mt = tile / p.n_blocks;
@@ -129,6 +139,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const int tap = it / p.cchunks;
                     const int cc = it - tap * p.cchunks;
                     mbar_wait(empty(stage), phase ^ 1);
+                    SKB_TR(0, it);
                     mbar_expect_tx(full(stage), (uint32_t)(p.a_box_bytes + Cfg::B_BYTES));
                     tma_load_5d(sA0 + stage * Cfg::A_BYTES, &tmA, full(stage), p.tap_coff[tap] + cc * BK,
                                 w0 + p.tap_dw[tap], p.tap_ph[tap], h0 + p.tap_dh[tap], n0);
@@ -145,14 +156,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
         int stage = 0, as = 0;
         uint32_t phase = 0, aphase = 0;
+        int tr_n = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             mbar_wait(tempty(as), aphase ^ 1);
             tc_fence_after();
+            if (lane == 0) SKB_TR(1, 1000);
             const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
             for (int it = 0; it < p.k_iters; ++it) {
                 mbar_wait(full(stage), phase);
                 tc_fence_after();
                 if (lane == 0) {
+                    SKB_TR(1, it);
                     const uint64_t ad = umma_desc(sA0 + stage * Cfg::A_BYTES, 16, SBO, SW);
                     const uint64_t bd = umma_desc(sB0 + stage * Cfg::B_BYTES, 16, SBO, SW);
 #pragma unroll
@@ -171,11 +185,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (as == 0) aphase ^= 1;
         }
     } else {
-        // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+        // ===================== epilogue (8 warps: TMEM lane quarter x column half) =====================
         constexpr int NB = Cfg::EPI_NB;
-        const int q = warp & 3;
+        constexpr int EPI_THREADS = 256;
+        const int q = warp & 3;                   // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;         // which half of the sub-tile's columns
         const int m = q * 32 + lane;              // accumulator row = pixel of the tile = TMEM lane
-        const int te = (int)threadIdx.x - 64;     // 0..127 within the epilogue group
+        const int te = (int)threadIdx.x - 64;     // 0..255 within the epilogue group
         const bool T0 = te == 0;                  // issues the TMA stores / residual prefetches
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const int hw = p.th * p.tw;
@@ -185,12 +201,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int wl = rem - hl * p.tw;
         const bool row_in_box = m < p.tn * hw;
         const int sub_cols = p.sub_cols;
+        const int wcols = sub_cols >> 1;          // columns per warp per sub-tile (32 or 16)
         const uint32_t row_bytes = (uint32_t)sub_cols * (p.out_f32 ? 4u : 2u);
         const uint32_t sw = row_bytes == 128 ? (uint32_t)(m & 7) : 0u;  // SWIZZLE_128B: 16 B chunk ^= row % 8
         const uint32_t row_off = (uint32_t)m * row_bytes;
+        const uint32_t chunk0 = (uint32_t)half * (row_bytes >> 5);  // first 16 B chunk of this warp's half
         uint32_t qseq = 0;  // running sub-tile number: ring slot = qseq % NB
         int as = 0;
         uint32_t aphase = 0;
+        int tr_n = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int nb = tile % p.n_blocks;
             int mt = tile / p.n_blocks;
@@ -206,24 +225,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 // ------------- smem-staged epilogue drained by TMA stores -------------
                 int nvalid = (p.cout - ncol0 + sub_cols - 1) / sub_cols;
                 nvalid = nvalid < 0 ? 0 : (nvalid > BN / sub_cols ? BN / sub_cols : nvalid);
-                for (int i = te; i < BN; i += 128) sts32f(sbias + 4u * i, __ldg(p.bias + ncol0 + i));
+                if (T0) SKB_TR(2, 100);
+                for (int i = te; i < BN; i += EPI_THREADS) sts32f(sbias + 4u * i, __ldg(p.bias + ncol0 + i));
                 if (T0 && nvalid > 0) {
                     tma_store_wait_read<NB - 1>();  // ring slot of the first sub-tile is drained
+                    SKB_TR(2, 101);
                     if (p.has_res) {
                         mbar_expect_tx(res_full(qseq % NB), (uint32_t)p.epi_box_bytes);
                         tma_load_4d(ebuf0 + (qseq % NB) * Cfg::EPI_BUF, &tmR, res_full(qseq % NB), ncol0, w0, h0, n0);
                     }
                 }
                 __syncwarp();
-                named_bar_sync(1, 128);  // bias visible, slot free
+                named_bar_sync(1, EPI_THREADS);  // bias visible, slot free
+                if (T0) SKB_TR(2, 102);
                 mbar_wait(tfull(as), aphase);
                 tc_fence_after();
+                if (T0) SKB_TR(2, 103);
                 for (int sub = 0; sub < nvalid; ++sub, ++qseq) {
                     const uint32_t slot_i = qseq % NB;
                     const uint32_t buf = ebuf0 + slot_i * Cfg::EPI_BUF;
                     const int c0 = sub * sub_cols;
                     if (T0) {
                         tma_store_wait_read<NB - 2>();  // slot of the NEXT sub-tile is drained
+                        SKB_TR(2, 104);
                         if (p.has_res && sub + 1 < nvalid) {
                             const uint32_t s2 = (qseq + 1) % NB;
                             mbar_expect_tx(res_full(s2), (uint32_t)p.epi_box_bytes);
@@ -231,57 +255,56 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                     }
                     __syncwarp();
-                    uint32_t v[64];
-                    {
-                        uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-                        tmem_ld32(acc + (uint32_t)c0, lo);
-                        if (sub_cols == 64) {
-                            uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-                            tmem_ld32(acc + (uint32_t)c0 + 32, hi);
-                        }
-                    }
+                    uint32_t v[32];
+                    const int cw = c0 + half * wcols;  // first accumulator column of this warp
+                    if (wcols == 32) tmem_ld32(acc + (uint32_t)cw, v);
+                    else tmem_ld16(acc + (uint32_t)cw, v);
                     tmem_ld_wait();
+                    if (T0) SKB_TR(2, 105);
                     if (sub == nvalid - 1) {  // accumulator fully drained into registers: hand TMEM back
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty(as));
                     }
                     if (p.has_res) mbar_wait(res_full(slot_i), (qseq / NB) & 1u);
+                    if (T0) SKB_TR(2, 106);
                     const uint32_t rowp = buf + row_off;
                     if (!p.out_f32) {
 #pragma unroll
-                        for (int j = 0; j < Cfg::SUBC_BF16 / 8; ++j) {
-                            float f[8];
+                        for (int j = 0; j < 4; ++j) {
+                            if (j * 8 < wcols) {
+                                float f[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j * 8 + i]) + lds32f(sbias + 4u * (c0 + j * 8 + i));
-                            if (p.act == SKB_ACT_SILU) {
+                                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j * 8 + i]) + lds32f(sbias + 4u * (cw + j * 8 + i));
+                                if (p.act == SKB_ACT_SILU) {
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) f[i] = silu_f(f[i]);
-                            } else if (p.act == SKB_ACT_RELU) {
+                                    for (int i = 0; i < 8; ++i) f[i] = silu_f(f[i]);
+                                } else if (p.act == SKB_ACT_RELU) {
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);
+                                    for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);
+                                }
+                                const uint32_t a16 = rowp + (((chunk0 + (uint32_t)j) ^ sw) << 4);
+                                if (p.has_res) {
+                                    const uint4 r = lds128(a16);
+                                    f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
+                                    f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
+                                    f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
+                                    f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+                                }
+                                uint4 o4;
+                                o4.x = pack_bf16x2(f[0], f[1]);
+                                o4.y = pack_bf16x2(f[2], f[3]);
+                                o4.z = pack_bf16x2(f[4], f[5]);
+                                o4.w = pack_bf16x2(f[6], f[7]);
+                                sts128(a16, o4);
                             }
-                            const uint32_t a16 = rowp + (((uint32_t)j ^ sw) << 4);
-                            if (p.has_res) {
-                                const uint4 r = lds128(a16);
-                                f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
-                                f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
-                                f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
-                                f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
-                            }
-                            uint4 o4;
-                            o4.x = pack_bf16x2(f[0], f[1]);
-                            o4.y = pack_bf16x2(f[2], f[3]);
-                            o4.z = pack_bf16x2(f[4], f[5]);
-                            o4.w = pack_bf16x2(f[6], f[7]);
-                            sts128(a16, o4);
                         }
-                    } else {
+                    } else {  // fp32 store: 16 columns per warp = 4 chunks of 4 floats
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
+                        for (int j = 0; j < 4; ++j) {
                             float f[4];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) f[i] = __uint_as_float(v[j * 4 + i]) + lds32f(sbias + 4u * (c0 + j * 4 + i));
+                            for (int i = 0; i < 4; ++i) f[i] = __uint_as_float(v[j * 4 + i]) + lds32f(sbias + 4u * (cw + j * 4 + i));
                             if (p.act == SKB_ACT_SILU) {
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) f[i] = silu_f(f[i]);
@@ -292,14 +315,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             uint4 o4;
                             o4.x = __float_as_uint(f[0]); o4.y = __float_as_uint(f[1]);
                             o4.z = __float_as_uint(f[2]); o4.w = __float_as_uint(f[3]);
-                            sts128(rowp + (((uint32_t)j ^ sw) << 4), o4);
+                            sts128(rowp + (((chunk0 + (uint32_t)j) ^ sw) << 4), o4);
                         }
                     }
+                    if (T0) SKB_TR(2, 107);
                     fence_proxy_async_smem();    // generic-proxy smem writes -> visible to the TMA engine
-                    named_bar_sync(1, 128);
+                    if (T0) SKB_TR(2, 108);
+                    named_bar_sync(1, EPI_THREADS);
                     if (T0) {
+                        SKB_TR(2, 109);
                         tma_store_4d(&tmY, buf, ncol0 + c0, w0, h0, n0);
                         tma_store_commit();
+                        SKB_TR(2, 110);
                     }
                     __syncwarp();
                 }
@@ -312,15 +339,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 // ------------- direct replicated stores (2x nearest upsample fused) -------------
                 const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
                 const bool valid = row_in_box && n < p.B && h < p.Ho && w < p.Wo;
+                const int cbeg = half * (BN / 2), cend = cbeg + BN / 2;  // BN >= 64 here: 32-column chunks split by half
                 const size_t opix = ((size_t)n * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w;
                 mbar_wait(tfull(as), aphase);
                 tc_fence_after();
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = (BN >= 64 ? cbeg : 0); c0 < (BN >= 64 ? cend : BN); c0 += 32) {
+                    if (BN < 64 && half) break;  // a 32-column tile has a single chunk: warps of half 1 only release
                     uint32_t v[32];
                     tmem_ld32(acc + (uint32_t)c0, v);
                     tmem_ld_wait();
-                    if (c0 + 32 >= BN) {
+                    if (c0 + 32 >= (BN >= 64 ? cend : BN)) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty(as));
@@ -369,6 +398,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
             }
+            if (p.up2 && BN < 64 && half) {  // idle half still owes its TMEM-release arrival
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty(as));
+            }
             as ^= 1;
             if (as == 0) aphase ^= 1;
         }
@@ -393,7 +427,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
         attr_set = true;
     }
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    conv_gemm_kernel<BN, BK><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, p);
+    conv_gemm_kernel<BN, BK><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, p);
     SKB_LAUNCH_CHECK();
     return SKB_OK;
 }
@@ -422,6 +456,14 @@ static void pick_tile(int B, int Ho, int Wo, int& tn, int& th, int& tw, int& til
 }  // namespace skb
 
 using namespace skb;
+
+static long long* g_conv_trace = nullptr;
+// Debug aid (not part of the drop-in surface): device buffer of 3*8192 int64 that CTA 0 of every
+// following conv launch fills with (event, clock64) pairs; pass NULL to switch tracing off.
+extern "C" int skb_debug_conv_trace(void* device_buffer) {
+    g_conv_trace = (long long*)device_buffer;
+    return SKB_OK;
+}
 
 extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const float* bias, const skb_view* residual,
                                const skb_view* y, int32_t cout_pad, int32_t ksize, int32_t stride, int32_t act,
@@ -499,6 +541,7 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
     p.res = residual ? (const __nv_bfloat16*)residual->ptr : nullptr;
     p.res_pitch = residual ? residual->pitch : 0;
     p.bias = bias; p.act = act;
+    p.trace = g_conv_trace;
     p.has_res = residual ? 1 : 0;
     if (residual) SKB_REQUIRE(y->dtype == SKB_BF16, SKB_ERR_UNSUPPORTED, "conv2d: residual needs a bf16 output");
     p.sub_cols = p.out_f32 ? 32 : (BN >= 64 ? 64 : 32);

@@ -82,6 +82,7 @@ _SIGNATURES = {
     "skb_device_check": (c_int32, []),
     "skb_conv2d_bf16": (c_int32, [POINTER(skb_view), c_void_p, c_void_p, POINTER(skb_view), POINTER(skb_view),
                                   c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "skb_debug_conv_trace": (c_int32, [c_void_p]),
     "skb_focus_nchw_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, POINTER(skb_view), c_void_p]),
     "skb_focus_nchw_u8": (c_int32, [c_void_p, c_int32, c_int32, c_int32, POINTER(skb_view), c_void_p]),
     "skb_maxpool5_bf16": (c_int32, [POINTER(skb_view), POINTER(skb_view), c_void_p]),
