@@ -61,7 +61,7 @@ int skb_device_check(void);
  * detector.py:215,219,224,228), nn.Conv2d 1x1 projections (attention.py:167-170; detector.py:56-59)
  * and the nn.Linear layers of TransformerLayer (attention.py:265,272-278).
  *   y = [residual +] act(conv(x, w) + bias)        (fp32 accumulate; bf16 or fp32 store)
- * x: bf16 view [N,H,W,Cin], Cin % 32 == 0.   w: bf16 [cout_pad][k*k][Cin] (K-major, BN folded),
+ * x: bf16 view [N,H,W,Cin], Cin % 16 == 0.   w: bf16 [cout_pad][k*k][Cin] (K-major, BN folded),
  * cout_pad % 32 == 0 (% 64 if > 32), rows >= y->c are zero.   bias: fp32 [cout_pad].
  * k in {1,3}, stride in {1,2} (pad k/2; stride 2 needs even H, W).  y: view [N,Ho,Wo,Cout] (or
  * [N,2Ho,2Wo,Cout] when upsample2x != 0: each result is replicated 2x2 = nearest upsampling fused
@@ -83,6 +83,21 @@ int skb_focus_nchw_f32(const float* img, int32_t n, int32_t h, int32_t w, const 
 /* Same for a uint8 image [N,3,H,W]: the caller's `img.float() / 255` (validate.py:237-238,
  * detect.py:133-134) is fused into the load, so the host ships 1 byte per sample over PCIe. */
 int skb_focus_nchw_u8(const uint8_t* img, int32_t n, int32_t h, int32_t w, const skb_view* y, void* stream);
+/* Whole FocusBlock.forward (blocks.py:170-182: four strided slices + cat + Conv-BN-SiLU k3 s1) in two
+ * launches.  (1) space-to-depth into a 16-channel NHWC scratch image whose rows carry one zero pixel on
+ * the left and three on the right; (2) the 3x3 conv as an implicit GEMM with K = 3 row taps x 64: the
+ * three horizontal taps of an output pixel are 96 CONTIGUOUS bytes of that scratch row, so the TMA
+ * tensor map uses a 128-byte window sliding by one 32-byte pixel (element stride < window) and each
+ * row tap is ONE full-width SWIZZLE_128B tile instead of three 32-byte-row tiles.
+ * img: fp32 or uint8 [N,3,H,W] (img_dtype SKB_F32, or SKB_U8 = scaled by 1/255, validate.py:237-238).
+ * w_rowtap: bf16 [cout_pad][3][4][16] (ky, kx slot 0..3 -- slot 3 zero --, focus channel 0..15 -- 12..15
+ * zero); see skyeye.engine.PackedFocusConv.  y: bf16 view [N,H/2,W/2,Cout].
+ * workspace: skb_focus_conv_workspace_bytes(n,h,w) bytes of scratch. */
+#define SKB_U8 2
+size_t skb_focus_conv_workspace_bytes(int32_t n, int32_t h, int32_t w);
+int skb_focus_conv_bf16(const void* img, int32_t img_dtype, int32_t n, int32_t h, int32_t w, const void* w_rowtap,
+                        const float* bias, const skb_view* y, int32_t cout_pad, int32_t act, void* workspace,
+                        size_t workspace_bytes, void* stream);
 /* nn.MaxPool2d(5, stride 1, pad 2) (blocks.py:143-144); SPP's 9 and 13 pools are cascades of it. */
 int skb_maxpool5_bf16(const skb_view* x, const skb_view* y, void* stream);
 /* CombinedAttention = ChannelAttention + SpatialAttention (attention.py:37-60, 80-98, 118-130).

@@ -14,6 +14,7 @@ from skyeye import engine as E  # noqa: E402
 
 # name: (B, H, W, Cin, Cout, k, stride, residual)
 CONV = {
+    "c3x3_focus_16_64_640": (16, 640, 640, 16, 64, 3, 1, False),
     "c3x3_128_160": (16, 160, 160, 128, 128, 3, 1, True),
     "c3x3_256_80": (16, 80, 80, 256, 256, 3, 1, True),
     "c3x3_512_40": (16, 40, 40, 512, 512, 3, 1, True),

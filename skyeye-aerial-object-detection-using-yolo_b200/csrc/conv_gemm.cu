@@ -11,15 +11,19 @@
 // * B operand: weights [Cout_pad][taps*Cin] bf16 (BN folded), 2-D tensor map, same swizzle.
 // * Accumulators: fp32 in TMEM, double buffered (2 x BN columns) so the epilogue of tile i overlaps
 //   the MMAs of tile i+1.  Persistent CTAs, static tile schedule (Cout block fastest).
-// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue
-//   (two warps per TMEM lane quarter, each taking half of the sub-tile's columns, so every SM
-//   sub-partition has two epilogue warps to overlap MUFU / smem / TMEM latencies):
-//   tcgen05.ld -> +bias (staged in smem) -> SiLU/ReLU -> +residual -> bf16/fp32, written into a ring
-//   of 16 KB swizzled smem sub-tiles (64 bf16 / 32 fp32 channels x 128 pixels) that one elected
-//   thread drains with TMA stores (coalesced, asynchronous, edge clipping for free) into a channel
-//   slice of the destination buffer.  The residual sub-tile is TMA-prefetched into the same ring
-//   slot one sub-tile ahead and updated in place.  (The two 2x-upsampling lateral convs keep a
-//   direct replicated-store epilogue.)
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = two epilogue
+//   groups of 4 warps.  Group g drains TMEM accumulator stage g, i.e. tiles alternate between the
+//   groups and two epilogues are in flight while the MMAs of a third tile run.  Each warp owns its
+//   TMEM lane quarter (32 pixels) and walks the columns in 32-column pieces:
+//   tcgen05.ld -> +bias (LDS.128 broadcast) -> SiLU as h + h*tanh(h) (one MUFU) / ReLU -> +residual ->
+//   bf16/fp32 (packed fp32x2 arithmetic), written into the group's ring of two 16 KB swizzled smem
+//   sub-tiles (64 bf16 / 32 fp32 channels x 128 pixels) that one elected thread drains with TMA stores
+//   (coalesced, asynchronous, edge clipping for free) into a channel slice of the destination buffer.
+//   The residual sub-tile is TMA-prefetched into the same ring slot one sub-tile ahead and updated in
+//   place.  (The two 2x-upsampling lateral convs keep a direct replicated-store epilogue.)
+// * Tile index -> (n-block, w, h, n) uses multiply-shift division: three runtime integer divisions per
+//   tile were ~800 cycles of serial latency on every role.
+// * K chunk = one swizzle span: 64 channels (SWIZZLE_128B), 32 (64B) or 16 (32B; the Focus conv).
 //
 // Replaces ConvolutionBlock.forward (skyeye/core/models/blocks.py:36-38) and friends, see
 // include/skyeye_b200.h.
@@ -27,10 +31,32 @@
 
 namespace skb {
 
+// n / d and n % d for a runtime divisor without the ~100-cycle integer-division sequence
+// (the per-tile coordinate decode sits on every role's critical path): n / d = umulhi(n, mul) >> shr.
+struct FastDiv {
+    uint32_t div, mul, shr;
+};
+static FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.div = (uint32_t)d;
+    if (d <= 1) { f.mul = 0; f.shr = 0; return f; }
+    int lg = 0;
+    while ((1u << lg) < (uint32_t)d) ++lg;  // ceil(log2 d)
+    const int pw = 31 + lg;
+    f.mul = (uint32_t)((((unsigned long long)1 << pw) + (unsigned long long)d - 1) / (unsigned long long)d);
+    f.shr = (uint32_t)(pw - 32);
+    return f;
+}
+__device__ __forceinline__ void fast_divmod(const FastDiv& f, int n, int& q, int& r) {  // 0 <= n < 2^31
+    q = f.div == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr);
+    r = n - q * (int)f.div;
+}
+
 struct ConvParams {
     int tiles_w, tiles_h, tiles_n;
     int tw, th, tn;
     int n_blocks, total_tiles;
+    FastDiv fd_nb, fd_tw, fd_th;  // divisors n_blocks, tiles_w, tiles_h of the tile index decode
     int B, Ho, Wo;
     int k_iters, cchunks;
     int a_box_bytes;
@@ -46,7 +72,7 @@ struct ConvParams {
     long long* trace;  // debug timeline of CTA 0 (null = off): [role][event] = clock64
 };
 
-// debug timeline: role 0 = producer, 1 = MMA, 2 = epilogue warp 2 lane 0; 4096 events per role
+// debug timeline: role 0 = producer, 1 = MMA, 2 = epilogue group 0 thread 0; 4096 events per role
 #define SKB_TR(role, ev)                                                                         \
     do {                                                                                         \
         if (p.trace && blockIdx.x == 0 && tr_n < 4096) { p.trace[(role) * 8192 + 2 * tr_n] = (ev); p.trace[(role) * 8192 + 2 * tr_n + 1] = clock64(); ++tr_n; } \
@@ -57,15 +83,69 @@ struct ConvCfg {
     static constexpr int A_BYTES = 128 * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int EPI_NB = 3;           // epilogue staging ring (sub-tiles)
+    static constexpr int EPI_GROUPS = 2;       // two 4-warp epilogue groups, one per TMEM accumulator stage
+    static constexpr int EPI_NB = 2;           // staging slots per group (sub-tiles)
     static constexpr int EPI_BUF = 16384;      // 128 rows x 128 B
-    static constexpr int EPI_BYTES = EPI_NB * EPI_BUF + BN * 4;
+    static constexpr int EPI_BYTES = EPI_GROUPS * EPI_NB * EPI_BUF + EPI_GROUPS * BN * 4;
     static constexpr int MAIN_BUDGET = 227 * 1024 - 1024 - 512 - EPI_BYTES;
     static constexpr int STAGES = (MAIN_BUDGET / STAGE_BYTES) < 8 ? (MAIN_BUDGET / STAGE_BYTES) : 8;
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // 64..512, power of two
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 512;
-    static constexpr int SUBC_BF16 = BN >= 64 ? 64 : 32;
 };
+
+__device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& nb, int& w0, int& h0, int& n0) {
+    int mt, iw, ih, in;
+    fast_divmod(p.fd_nb, tile, mt, nb);
+    fast_divmod(p.fd_tw, mt, mt, iw);
+    fast_divmod(p.fd_th, mt, in, ih);
+    w0 = iw * p.tw; h0 = ih * p.th; n0 = in * p.tn;
+}
+
+// bias + activation (+ residual) on 8 accumulator columns -> one 16-byte chunk of bf16
+__device__ __forceinline__ void epi_chunk_bf16(const uint32_t* v, uint32_t bias_addr, int act, bool has_res, uint32_t a16) {
+    const float4 b0 = lds128f(bias_addr), b1 = lds128f(bias_addr + 16u);
+    float2 x0 = fadd2(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(b0.x, b0.y));
+    float2 x1 = fadd2(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(b0.z, b0.w));
+    float2 x2 = fadd2(make_float2(__uint_as_float(v[4]), __uint_as_float(v[5])), make_float2(b1.x, b1.y));
+    float2 x3 = fadd2(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(b1.z, b1.w));
+    if (act == SKB_ACT_SILU) {
+        x0 = silu2_tanh(x0); x1 = silu2_tanh(x1); x2 = silu2_tanh(x2); x3 = silu2_tanh(x3);
+    } else if (act == SKB_ACT_RELU) {
+        x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f);
+        x2.x = fmaxf(x2.x, 0.f); x2.y = fmaxf(x2.y, 0.f); x3.x = fmaxf(x3.x, 0.f); x3.y = fmaxf(x3.y, 0.f);
+    }
+    if (has_res) {
+        const uint4 r = lds128(a16);
+        x0 = fadd2(x0, make_float2(bf16_lo(r.x), bf16_hi(r.x)));
+        x1 = fadd2(x1, make_float2(bf16_lo(r.y), bf16_hi(r.y)));
+        x2 = fadd2(x2, make_float2(bf16_lo(r.z), bf16_hi(r.z)));
+        x3 = fadd2(x3, make_float2(bf16_lo(r.w), bf16_hi(r.w)));
+    }
+    uint4 o4;
+    o4.x = pack_bf16x2(x0.x, x0.y);
+    o4.y = pack_bf16x2(x1.x, x1.y);
+    o4.z = pack_bf16x2(x2.x, x2.y);
+    o4.w = pack_bf16x2(x3.x, x3.y);
+    sts128(a16, o4);
+}
+// bias + activation on 4 accumulator columns -> one 16-byte chunk of fp32 (precise SiLU)
+__device__ __forceinline__ void epi_chunk_f32(const uint32_t* v, uint32_t bias_addr, int act, uint32_t a16) {
+    const float4 b0 = lds128f(bias_addr);
+    float f[4];
+    f[0] = __uint_as_float(v[0]) + b0.x; f[1] = __uint_as_float(v[1]) + b0.y;
+    f[2] = __uint_as_float(v[2]) + b0.z; f[3] = __uint_as_float(v[3]) + b0.w;
+    if (act == SKB_ACT_SILU) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f[i] = silu_f(f[i]);
+    } else if (act == SKB_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f[i] = fmaxf(f[i], 0.0f);
+    }
+    uint4 o4;
+    o4.x = __float_as_uint(f[0]); o4.y = __float_as_uint(f[1]);
+    o4.z = __float_as_uint(f[2]); o4.w = __float_as_uint(f[3]);
+    sts128(a16, o4);
+}
 
 template <int BN, int BK>
 __global__ void __launch_bounds__(320, 1)
@@ -73,8 +153,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const ConvParams p) {
     using Cfg = ConvCfg<BN, BK>;
     constexpr int STAGES = Cfg::STAGES;
-    constexpr uint32_t SW = BK == 64 ? UMMA_SW128 : UMMA_SW64;
+    constexpr uint32_t SW = BK == 64 ? UMMA_SW128 : (BK == 32 ? UMMA_SW64 : UMMA_SW32);
     constexpr uint32_t SBO = 8 * BK * 2;  // bytes between 8-row groups
+    constexpr int NB = Cfg::EPI_NB;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -82,14 +163,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t sA0 = base;
     const uint32_t sB0 = base + STAGES * Cfg::A_BYTES;
     const uint32_t ebuf0 = base + STAGES * Cfg::STAGE_BYTES;
-    const uint32_t sbias = ebuf0 + Cfg::EPI_NB * Cfg::EPI_BUF;
-    const uint32_t bar0 = sbias + BN * 4;
+    const uint32_t sbias = ebuf0 + Cfg::EPI_GROUPS * NB * Cfg::EPI_BUF;
+    const uint32_t bar0 = sbias + Cfg::EPI_GROUPS * BN * 4;
     auto full = [&](int s) { return bar0 + 8u * s; };
     auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
     auto tfull = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
     auto tempty = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
     auto res_full = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + s); };
-    const uint32_t slot = bar0 + 8u * (2 * STAGES + 4 + Cfg::EPI_NB);
+    const uint32_t slot = bar0 + 8u * (2 * STAGES + 4 + Cfg::EPI_GROUPS * NB);
     volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -108,9 +189,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(tfull(s), 1);
-                mbar_init(tempty(s), 8);
+                mbar_init(tempty(s), 4);
             }
-            for (int s = 0; s < Cfg::EPI_NB; ++s) mbar_init(res_full(s), 1);
+            for (int s = 0; s < Cfg::EPI_GROUPS * NB; ++s) mbar_init(res_full(s), 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -128,13 +209,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t phase = 0;
             int tr_n = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int nb = tile % p.n_blocks;
-                int mt = tile / p.n_blocks;
-                const int iw = mt % p.tiles_w;
-                mt /= p.tiles_w;
-                const int ih = mt % p.tiles_h;
-                const int in = mt / p.tiles_h;
-                const int w0 = iw * p.tw, h0 = ih * p.th, n0 = in * p.tn;
+                int nb, w0, h0, n0;
+                decode_tile(p, tile, nb, w0, h0, n0);
                 for (int it = 0; it < p.k_iters; ++it) {
                     const int tap = it / p.cchunks;
                     const int cc = it - tap * p.cchunks;
@@ -185,188 +261,170 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (as == 0) aphase ^= 1;
         }
     } else {
-        // ===================== epilogue (8 warps: TMEM lane quarter x column half) =====================
-        constexpr int NB = Cfg::EPI_NB;
-        constexpr int EPI_THREADS = 256;
-        const int q = warp & 3;                   // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;         // which half of the sub-tile's columns
-        const int m = q * 32 + lane;              // accumulator row = pixel of the tile = TMEM lane
-        const int te = (int)threadIdx.x - 64;     // 0..255 within the epilogue group
-        const bool T0 = te == 0;                  // issues the TMA stores / residual prefetches
+        // ===================== epilogue: two groups of 4 warps, group g drains TMEM stage g =====================
+        // (tiles alternate between the groups, so the epilogue of one tile overlaps the epilogue of the
+        // next one as well as the MMAs of the one after; each warp owns 32 accumulator rows = its TMEM
+        // lane quarter and walks the tile's columns in 32-column pieces)
+        constexpr int GT = 128;                    // threads per group
+        const int g = (warp - 2) >> 2;
+        const int q = warp & 3;                    // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;               // accumulator row = pixel of the tile = TMEM lane
+        const int tg = (int)threadIdx.x - 64 - g * GT;
+        const bool T0 = tg == 0;                   // issues the group's TMA stores / residual prefetches
+        const int barid = 1 + g;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        const int hw = p.th * p.tw;
-        const int nl = m / hw;
-        const int rem = m - nl * hw;
-        const int hl = rem / p.tw;
-        const int wl = rem - hl * p.tw;
-        const bool row_in_box = m < p.tn * hw;
+        const uint32_t ebuf_g = ebuf0 + (uint32_t)(g * NB) * Cfg::EPI_BUF;
+        const uint32_t sbias_g = sbias + (uint32_t)(g * BN) * 4u;
         const int sub_cols = p.sub_cols;
-        const int wcols = sub_cols >> 1;          // columns per warp per sub-tile (32 or 16)
         const uint32_t row_bytes = (uint32_t)sub_cols * (p.out_f32 ? 4u : 2u);
         const uint32_t sw = row_bytes == 128 ? (uint32_t)(m & 7) : 0u;  // SWIZZLE_128B: 16 B chunk ^= row % 8
         const uint32_t row_off = (uint32_t)m * row_bytes;
-        const uint32_t chunk0 = (uint32_t)half * (row_bytes >> 5);  // first 16 B chunk of this warp's half
-        uint32_t qseq = 0;  // running sub-tile number: ring slot = qseq % NB
-        int as = 0;
+        const uint32_t acc = tmem_base + lane_addr + (uint32_t)(g * BN);
+        const int step = 2 * (int)gridDim.x;
+        uint32_t qseq = 0;  // running sub-tile number of this group: staging slot = qseq % NB
         uint32_t aphase = 0;
         int tr_n = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int nb = tile % p.n_blocks;
-            int mt = tile / p.n_blocks;
-            const int iw = mt % p.tiles_w;
-            mt /= p.tiles_w;
-            const int ih = mt % p.tiles_h;
-            const int in = mt / p.tiles_h;
-            const int w0 = iw * p.tw, h0 = ih * p.th, n0 = in * p.tn;
-            const int ncol0 = nb * BN;
-            const uint32_t acc = tmem_base + lane_addr + (uint32_t)(as * BN);
+        int tile = (int)blockIdx.x + g * (int)gridDim.x;
 
-            if (!p.up2) {
-                // ------------- smem-staged epilogue drained by TMA stores -------------
-                int nvalid = (p.cout - ncol0 + sub_cols - 1) / sub_cols;
-                nvalid = nvalid < 0 ? 0 : (nvalid > BN / sub_cols ? BN / sub_cols : nvalid);
-                if (T0) SKB_TR(2, 100);
-                for (int i = te; i < BN; i += EPI_THREADS) sts32f(sbias + 4u * i, __ldg(p.bias + ncol0 + i));
-                if (T0 && nvalid > 0) {
-                    tma_store_wait_read<NB - 1>();  // ring slot of the first sub-tile is drained
-                    SKB_TR(2, 101);
-                    if (p.has_res) {
-                        mbar_expect_tx(res_full(qseq % NB), (uint32_t)p.epi_box_bytes);
-                        tma_load_4d(ebuf0 + (qseq % NB) * Cfg::EPI_BUF, &tmR, res_full(qseq % NB), ncol0, w0, h0, n0);
-                    }
+        if (!p.up2) {
+            auto n_sub = [&](int nb) {
+                int nv = (p.cout - nb * BN + sub_cols - 1) / sub_cols;
+                return nv < 0 ? 0 : (nv > BN / sub_cols ? BN / sub_cols : nv);
+            };
+            auto load_bias = [&](int nb) {
+                for (int i = tg; i < BN; i += GT) sts32f(sbias_g + 4u * i, __ldg(p.bias + nb * BN + i));
+            };
+            if (p.n_blocks == 1) load_bias(0);
+            if (T0 && p.has_res && tile < p.total_tiles) {  // residual of the very first sub-tile
+                int nb, w0, h0, n0;
+                decode_tile(p, tile, nb, w0, h0, n0);
+                if (n_sub(nb) > 0) {
+                    mbar_expect_tx(res_full(g * NB), (uint32_t)p.epi_box_bytes);
+                    tma_load_4d(ebuf_g, &tmR, res_full(g * NB), nb * BN, w0, h0, n0);
                 }
-                __syncwarp();
-                named_bar_sync(1, EPI_THREADS);  // bias visible, slot free
-                if (T0) SKB_TR(2, 102);
-                mbar_wait(tfull(as), aphase);
+            }
+            named_bar_sync(barid, GT);
+            for (; tile < p.total_tiles; tile += step) {
+                int nb, w0, h0, n0;
+                decode_tile(p, tile, nb, w0, h0, n0);
+                const int ncol0 = nb * BN;
+                const int nvalid = n_sub(nb);
+                if (T0 && g == 0) SKB_TR(2, 100);
+                if (p.n_blocks > 1) {  // the previous tile's last barrier ordered every read of the old bias
+                    load_bias(nb);
+                    named_bar_sync(barid, GT);
+                }
+                mbar_wait(tfull(g), aphase);
                 tc_fence_after();
-                if (T0) SKB_TR(2, 103);
+                if (T0 && g == 0) SKB_TR(2, 103);
                 for (int sub = 0; sub < nvalid; ++sub, ++qseq) {
                     const uint32_t slot_i = qseq % NB;
-                    const uint32_t buf = ebuf0 + slot_i * Cfg::EPI_BUF;
+                    const uint32_t buf = ebuf_g + slot_i * Cfg::EPI_BUF;
                     const int c0 = sub * sub_cols;
-                    if (T0) {
-                        tma_store_wait_read<NB - 2>();  // slot of the NEXT sub-tile is drained
-                        SKB_TR(2, 104);
-                        if (p.has_res && sub + 1 < nvalid) {
-                            const uint32_t s2 = (qseq + 1) % NB;
-                            mbar_expect_tx(res_full(s2), (uint32_t)p.epi_box_bytes);
-                            tma_load_4d(ebuf0 + s2 * Cfg::EPI_BUF, &tmR, res_full(s2), ncol0 + c0 + sub_cols, w0, h0, n0);
-                        }
-                    }
-                    __syncwarp();
-                    uint32_t v[32];
-                    const int cw = c0 + half * wcols;  // first accumulator column of this warp
-                    if (wcols == 32) tmem_ld32(acc + (uint32_t)cw, v);
-                    else tmem_ld16(acc + (uint32_t)cw, v);
-                    tmem_ld_wait();
-                    if (T0) SKB_TR(2, 105);
-                    if (sub == nvalid - 1) {  // accumulator fully drained into registers: hand TMEM back
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty(as));
-                    }
-                    if (p.has_res) mbar_wait(res_full(slot_i), (qseq / NB) & 1u);
-                    if (T0) SKB_TR(2, 106);
                     const uint32_t rowp = buf + row_off;
+                    const bool last = sub == nvalid - 1;
+                    if (p.has_res) mbar_wait(res_full(g * NB + slot_i), (qseq / NB) & 1u);
                     if (!p.out_f32) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (j * 8 < wcols) {
-                                float f[8];
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j * 8 + i]) + lds32f(sbias + 4u * (cw + j * 8 + i));
-                                if (p.act == SKB_ACT_SILU) {
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) f[i] = silu_f(f[i]);
-                                } else if (p.act == SKB_ACT_RELU) {
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);
-                                }
-                                const uint32_t a16 = rowp + (((chunk0 + (uint32_t)j) ^ sw) << 4);
-                                if (p.has_res) {
-                                    const uint4 r = lds128(a16);
-                                    f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x);
-                                    f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
-                                    f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z);
-                                    f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
-                                }
-                                uint4 o4;
-                                o4.x = pack_bf16x2(f[0], f[1]);
-                                o4.y = pack_bf16x2(f[2], f[3]);
-                                o4.z = pack_bf16x2(f[4], f[5]);
-                                o4.w = pack_bf16x2(f[6], f[7]);
-                                sts128(a16, o4);
+                        const int pieces = sub_cols >> 5;  // 32 accumulator columns = 4 chunks of 8 bf16
+                        for (int hh = 0; hh < pieces; ++hh) {
+                            uint32_t v[32];
+                            tmem_ld32(acc + (uint32_t)(c0 + hh * 32), v);
+                            tmem_ld_wait();
+                            if (last && hh == pieces - 1) {  // accumulator fully read: hand the TMEM stage back
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(tempty(g));
                             }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                epi_chunk_bf16(v + j * 8, sbias_g + 4u * (uint32_t)(c0 + hh * 32 + j * 8), p.act, p.has_res != 0,
+                                               rowp + ((((uint32_t)(hh * 4 + j)) ^ sw) << 4));
                         }
-                    } else {  // fp32 store: 16 columns per warp = 4 chunks of 4 floats
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float f[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) f[i] = __uint_as_float(v[j * 4 + i]) + lds32f(sbias + 4u * (cw + j * 4 + i));
-                            if (p.act == SKB_ACT_SILU) {
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) f[i] = silu_f(f[i]);
-                            } else if (p.act == SKB_ACT_RELU) {
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) f[i] = fmaxf(f[i], 0.0f);
-                            }
-                            uint4 o4;
-                            o4.x = __float_as_uint(f[0]); o4.y = __float_as_uint(f[1]);
-                            o4.z = __float_as_uint(f[2]); o4.w = __float_as_uint(f[3]);
-                            sts128(rowp + (((chunk0 + (uint32_t)j) ^ sw) << 4), o4);
+                    } else {  // fp32 store: 32 columns per sub-tile = 8 chunks of 4 floats
+                        uint32_t v[32];
+                        tmem_ld32(acc + (uint32_t)c0, v);
+                        tmem_ld_wait();
+                        if (last) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(tempty(g));
                         }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            epi_chunk_f32(v + j * 4, sbias_g + 4u * (uint32_t)(c0 + j * 4), p.act, rowp + ((((uint32_t)j) ^ sw) << 4));
                     }
-                    if (T0) SKB_TR(2, 107);
-                    fence_proxy_async_smem();    // generic-proxy smem writes -> visible to the TMA engine
-                    if (T0) SKB_TR(2, 108);
-                    named_bar_sync(1, EPI_THREADS);
+                    if (T0) tma_store_wait_read<0>();  // the group's previous store has drained the OTHER slot
+                    fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the TMA engine
+                    named_bar_sync(barid, GT);
                     if (T0) {
-                        SKB_TR(2, 109);
                         tma_store_4d(&tmY, buf, ncol0 + c0, w0, h0, n0);
                         tma_store_commit();
-                        SKB_TR(2, 110);
+                        if (g == 0) SKB_TR(2, 110);
+                        if (p.has_res) {  // prefetch the residual of the group's next sub-tile into the other slot
+                            const uint32_t s2 = (qseq + 1) % NB;
+                            int nb2 = nb, w2 = w0, h2 = h0, n2 = n0, c2 = c0 + sub_cols;
+                            bool have = !last;
+                            if (last && tile + step < p.total_tiles) {
+                                decode_tile(p, tile + step, nb2, w2, h2, n2);
+                                c2 = 0;
+                                have = n_sub(nb2) > 0;
+                            }
+                            if (have) {
+                                mbar_expect_tx(res_full(g * NB + s2), (uint32_t)p.epi_box_bytes);
+                                tma_load_4d(ebuf_g + s2 * Cfg::EPI_BUF, &tmR, res_full(g * NB + s2), nb2 * BN + c2, w2, h2, n2);
+                            }
+                        }
                     }
                     __syncwarp();
                 }
                 if (nvalid == 0) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty(as));
+                    if (lane == 0) mbar_arrive(tempty(g));
                 }
-            } else {
-                // ------------- direct replicated stores (2x nearest upsample fused) -------------
+                aphase ^= 1;
+            }
+            if (T0) tma_store_wait_all();
+        } else {
+            // ------------- direct replicated stores (2x nearest upsample fused) -------------
+            const int hw = p.th * p.tw;
+            const int nl = m / hw;
+            const int rem = m - nl * hw;
+            const int hl = rem / p.tw;
+            const int wl = rem - hl * p.tw;
+            const bool row_in_box = m < p.tn * hw;
+            for (; tile < p.total_tiles; tile += step) {
+                int nb, w0, h0, n0;
+                decode_tile(p, tile, nb, w0, h0, n0);
+                const int ncol0 = nb * BN;
                 const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
                 const bool valid = row_in_box && n < p.B && h < p.Ho && w < p.Wo;
-                const int cbeg = half * (BN / 2), cend = cbeg + BN / 2;  // BN >= 64 here: 32-column chunks split by half
                 const size_t opix = ((size_t)n * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w;
-                mbar_wait(tfull(as), aphase);
+                mbar_wait(tfull(g), aphase);
                 tc_fence_after();
 #pragma unroll 1
-                for (int c0 = (BN >= 64 ? cbeg : 0); c0 < (BN >= 64 ? cend : BN); c0 += 32) {
-                    if (BN < 64 && half) break;  // a 32-column tile has a single chunk: warps of half 1 only release
+                for (int c0 = 0; c0 < BN; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(acc + (uint32_t)c0, v);
                     tmem_ld_wait();
-                    if (c0 + 32 >= (BN >= 64 ? cend : BN)) {
+                    if (c0 + 32 >= BN) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty(as));
+                        if (lane == 0) mbar_arrive(tempty(g));
                     }
                     const int ncol = ncol0 + c0;
                     if (valid) {
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const int col = ncol + g * 8;
+                        for (int gg = 0; gg < 4; ++gg) {
+                            const int col = ncol + gg * 8;
                             if (col < p.cout) {
                                 const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
                                 const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
                                 float f[8];
-                                f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
-                                f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
-                                f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
-                                f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+                                f[0] = __uint_as_float(v[gg * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[gg * 8 + 1]) + b0.y;
+                                f[2] = __uint_as_float(v[gg * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[gg * 8 + 3]) + b0.w;
+                                f[4] = __uint_as_float(v[gg * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[gg * 8 + 5]) + b1.y;
+                                f[6] = __uint_as_float(v[gg * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[gg * 8 + 7]) + b1.w;
                                 if (p.act == SKB_ACT_SILU) {
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
@@ -397,16 +455,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                     }
                 }
+                aphase ^= 1;
             }
-            if (p.up2 && BN < 64 && half) {  // idle half still owes its TMEM-release arrival
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty(as));
-            }
-            as ^= 1;
-            if (as == 0) aphase ^= 1;
         }
-        if (T0) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -475,7 +526,7 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
     SKB_REQUIRE(ksize == 1 || ksize == 3, SKB_ERR_UNSUPPORTED, "conv2d: kernel size %d (only 1 and 3 are on the path)", ksize);
     SKB_REQUIRE(stride == 1 || stride == 2, SKB_ERR_UNSUPPORTED, "conv2d: stride %d", stride);
     const int Cin = x->c;
-    SKB_REQUIRE(Cin % 32 == 0 && Cin >= 32, SKB_ERR_ARG, "conv2d: Cin=%d must be a multiple of 32 (pad the producer)", Cin);
+    SKB_REQUIRE(Cin % 16 == 0 && Cin >= 16, SKB_ERR_ARG, "conv2d: Cin=%d must be a multiple of 16 (pad the producer)", Cin);
     SKB_REQUIRE(x->pitch % 8 == 0 && ((uintptr_t)x->ptr & 15) == 0, SKB_ERR_ARG, "conv2d: input view must be 16B aligned (pitch %d)", x->pitch);
     SKB_REQUIRE(cout_pad % 32 == 0 && (cout_pad == 32 || cout_pad % 64 == 0), SKB_ERR_ARG, "conv2d: cout_pad=%d", cout_pad);
     SKB_REQUIRE(y->c % 8 == 0 && y->c <= cout_pad, SKB_ERR_ARG, "conv2d: y->c=%d must be a multiple of 8 and <= cout_pad", y->c);
@@ -492,7 +543,7 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
                         residual->c >= y->c && residual->pitch % 8 == 0 && ((uintptr_t)residual->ptr & 15) == 0,
                     SKB_ERR_ARG, "conv2d: residual view mismatch");
     }
-    const int BK = (Cin % 64 == 0) ? 64 : 32;
+    const int BK = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);  // K chunk = swizzle span (128 / 64 / 32 B rows)
     const int taps = ksize * ksize;
 
     ConvParams p;
@@ -520,6 +571,7 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
     }
     p.n_blocks = cout_pad / BN;
     p.total_tiles = m_tiles * p.n_blocks;
+    p.fd_nb = make_fastdiv(p.n_blocks); p.fd_tw = make_fastdiv(p.tiles_w); p.fd_th = make_fastdiv(p.tiles_h);
     p.B = x->n; p.Ho = Ho; p.Wo = Wo;
     p.cchunks = Cin / BK;
     p.k_iters = taps * p.cchunks;
@@ -594,7 +646,85 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
     if (BN == bn && BK == bk) return launch_conv<bn, bk>(tmA, tmB, tmY, tmR, p, st);
     SKB_CONV_CASE(256, 64) SKB_CONV_CASE(128, 64) SKB_CONV_CASE(64, 64) SKB_CONV_CASE(32, 64)
     SKB_CONV_CASE(256, 32) SKB_CONV_CASE(128, 32) SKB_CONV_CASE(64, 32) SKB_CONV_CASE(32, 32)
+    SKB_CONV_CASE(256, 16) SKB_CONV_CASE(128, 16) SKB_CONV_CASE(64, 16) SKB_CONV_CASE(32, 16)
 #undef SKB_CONV_CASE
     set_error("conv2d: no kernel for BN=%d BK=%d", BN, BK);
     return SKB_ERR_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FocusBlock as (padded space-to-depth) + (row-tap implicit GEMM over sliding 128-byte windows)
+// ---------------------------------------------------------------------------------------------
+namespace skb {
+int launch_focus_pad(const void* img, int img_dtype, int n, int h, int w, void* scratch, cudaStream_t st);
+}
+
+extern "C" size_t skb_focus_conv_workspace_bytes(int32_t n, int32_t h, int32_t w) {
+    if (n <= 0 || h <= 0 || w <= 0) return 256;
+    return (size_t)n * (h / 2) * (w / 2 + 4) * 16 * 2 + 256;
+}
+
+extern "C" int skb_focus_conv_bf16(const void* img, int32_t img_dtype, int32_t n, int32_t h, int32_t w, const void* w_rowtap,
+                                   const float* bias, const skb_view* y, int32_t cout_pad, int32_t act, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+    int rc = check_device();
+    if (rc != SKB_OK) return rc;
+    SKB_REQUIRE(img && w_rowtap && bias && y && y->ptr && workspace, SKB_ERR_ARG, "focus_conv: null argument");
+    SKB_REQUIRE(img_dtype == SKB_F32 || img_dtype == SKB_U8, SKB_ERR_ARG, "focus_conv: image dtype must be SKB_F32 or SKB_U8");
+    SKB_REQUIRE(n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, SKB_ERR_ARG, "focus_conv: H, W must be even (got %dx%d)", h, w);
+    SKB_REQUIRE(((uintptr_t)img & (img_dtype == SKB_F32 ? 7 : 1)) == 0, SKB_ERR_ARG, "focus_conv: image alignment");
+    const int Ho = h / 2, Wo = w / 2, Wp = Wo + 4;
+    SKB_REQUIRE(y->dtype == SKB_BF16 && y->n == n && y->h == Ho && y->w == Wo, SKB_ERR_ARG, "focus_conv: output view [%d,%d,%d] != [%d,%d,%d]",
+                y->n, y->h, y->w, n, Ho, Wo);
+    SKB_REQUIRE(cout_pad % 32 == 0 && (cout_pad == 32 || cout_pad % 64 == 0), SKB_ERR_ARG, "focus_conv: cout_pad=%d", cout_pad);
+    SKB_REQUIRE(y->c % 8 == 0 && y->c <= cout_pad && y->pitch % 8 == 0 && ((uintptr_t)y->ptr & 15) == 0, SKB_ERR_ARG, "focus_conv: output view alignment");
+    SKB_REQUIRE(((uintptr_t)w_rowtap & 15) == 0 && ((uintptr_t)bias & 15) == 0, SKB_ERR_ARG, "focus_conv: weight/bias alignment");
+    SKB_REQUIRE(workspace_bytes >= skb_focus_conv_workspace_bytes(n, h, w), SKB_ERR_WORKSPACE, "focus_conv: workspace too small");
+    void* scratch = (void*)(((uintptr_t)workspace + 127) & ~(uintptr_t)127);
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = launch_focus_pad(img, img_dtype, n, h, w, scratch, st);
+    if (rc != SKB_OK) return rc;
+
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    pick_tile(n, Ho, Wo, p.tn, p.th, p.tw, p.total_tiles);
+    p.tiles_w = cdiv(Wo, p.tw); p.tiles_h = cdiv(Ho, p.th); p.tiles_n = cdiv(n, p.tn);
+    const int m_tiles = p.total_tiles;
+    const int BN = cout_pad % 128 == 0 ? 128 : (cout_pad % 64 == 0 ? 64 : 32);
+    p.n_blocks = cout_pad / BN;
+    p.total_tiles = m_tiles * p.n_blocks;
+    p.fd_nb = make_fastdiv(p.n_blocks); p.fd_tw = make_fastdiv(p.tiles_w); p.fd_th = make_fastdiv(p.tiles_h);
+    p.B = n; p.Ho = Ho; p.Wo = Wo;
+    p.cchunks = 1; p.k_iters = 3;
+    p.a_box_bytes = p.tn * p.th * p.tw * 64 * 2;
+    for (int t = 0; t < 3; ++t) { p.tap_dh[t] = t - 1; p.tap_dw[t] = 0; p.tap_ph[t] = 0; p.tap_coff[t] = 0; }
+    p.out = y->ptr; p.out_pitch = y->pitch; p.out_f32 = 0; p.cout = y->c; p.up2 = 0;
+    p.bias = bias; p.act = act; p.trace = g_conv_trace;
+    p.sub_cols = BN >= 64 ? 64 : 32;
+    const int row_bytes = p.sub_cols * 2;
+    p.epi_box_bytes = p.tn * p.th * p.tw * row_bytes;
+
+    CUtensorMap tmA, tmB, tmY;
+    {
+        // window (n, oy, ox) = scratch pixels ox .. ox+3 of the padded row = image pixels ox-1 .. ox+2:
+        // 64 elements whose start advances by ONE pixel (32 B) per w step -> overlapping 128-byte rows
+        uint64_t dims[5] = {64, (uint64_t)Wo, 1, (uint64_t)Ho, (uint64_t)n};
+        uint64_t str[4] = {32, (uint64_t)Wp * 32, (uint64_t)Wp * 32, (uint64_t)Wp * 32 * Ho};
+        uint32_t box[5] = {64u, (uint32_t)p.tw, 1u, (uint32_t)p.th, (uint32_t)p.tn};
+        rc = encode_tensor_map(&tmA, scratch, 2, 5, dims, str, box, 128);
+        if (rc != SKB_OK) return rc;
+        uint64_t bd[2] = {192, (uint64_t)cout_pad};
+        uint64_t bs[1] = {192 * 2};
+        uint32_t bb[2] = {64u, (uint32_t)BN};
+        rc = encode_tensor_map(&tmB, w_rowtap, 2, 2, bd, bs, bb, 128);
+        if (rc != SKB_OK) return rc;
+        uint64_t yd[4] = {(uint64_t)y->c, (uint64_t)y->w, (uint64_t)y->h, (uint64_t)y->n};
+        uint64_t ys[3] = {(uint64_t)y->pitch * 2, (uint64_t)y->pitch * 2 * y->w, (uint64_t)y->pitch * 2 * y->w * y->h};
+        uint32_t yb[4] = {(uint32_t)p.sub_cols, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
+        rc = encode_tensor_map(&tmY, y->ptr, 2, 4, yd, ys, yb, row_bytes == 128 ? 128 : 0);
+        if (rc != SKB_OK) return rc;
+    }
+    if (BN == 128) return launch_conv<128, 64>(tmA, tmB, tmY, tmB, p, st);
+    if (BN == 64) return launch_conv<64, 64>(tmA, tmB, tmY, tmB, p, st);
+    return launch_conv<32, 64>(tmA, tmB, tmY, tmB, p, st);
 }

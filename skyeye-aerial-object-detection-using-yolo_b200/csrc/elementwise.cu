@@ -68,6 +68,35 @@ __global__ void focus_kernel(const T* __restrict__ img, int N, int H, int W, __n
     }
 }
 
+// Same space-to-depth into the padded 16-channel scratch of skb_focus_conv_bf16: row = [0 | Wo pixels | 0 0 0]
+template <typename T>
+__global__ void focus_pad_kernel(const T* __restrict__ img, int N, int H, int W, __nv_bfloat16* __restrict__ y) {
+    const int Ho = H / 2, Wo = W / 2, Wp = Wo + 4;
+    const long total = (long)N * Ho * Wp;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int col = (int)(i % Wp);
+        const int oy = (int)((i / Wp) % Ho);
+        const int n = (int)(i / ((long)Wp * Ho));
+        uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+        const int ox = col - 1;
+        if (ox >= 0 && ox < Wo) {
+            float v[12];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const T* base = img + (((long)n * 3 + c) * H + 2 * oy) * W + 2 * ox;
+                const float2 top = focus_ld2(base);
+                const float2 bot = focus_ld2(base + W);
+                v[0 * 3 + c] = top.x; v[1 * 3 + c] = bot.x; v[2 * 3 + c] = top.y; v[3 * 3 + c] = bot.y;
+            }
+            a.x = pack_bf16x2(v[0], v[1]); a.y = pack_bf16x2(v[2], v[3]); a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
+            b.x = pack_bf16x2(v[8], v[9]); b.y = pack_bf16x2(v[10], v[11]);
+        }
+        uint4* o = reinterpret_cast<uint4*>(y + i * 16);
+        o[0] = a;
+        o[1] = b;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // MaxPool2d(5, 1, 2) on bf16 NHWC (padding acts as -inf)
 // ---------------------------------------------------------------------------------------------
@@ -420,6 +449,18 @@ extern "C" int skb_focus_nchw_u8(const uint8_t* img, int32_t n, int32_t h, int32
     SKB_LAUNCH_CHECK();
     return SKB_OK;
 }
+
+namespace skb {
+int launch_focus_pad(const void* img, int img_dtype, int n, int h, int w, void* scratch, cudaStream_t st) {
+    const long total = (long)n * (h / 2) * (w / 2 + 4);
+    if (img_dtype == SKB_F32)
+        focus_pad_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)img, n, h, w, (__nv_bfloat16*)scratch);
+    else
+        focus_pad_kernel<uint8_t><<<grid_for(total, 256), 256, 0, st>>>((const uint8_t*)img, n, h, w, (__nv_bfloat16*)scratch);
+    SKB_LAUNCH_CHECK();
+    return SKB_OK;
+}
+}  // namespace skb
 
 extern "C" int skb_maxpool5_bf16(const skb_view* x, const skb_view* y, void* stream) {
     int rc = check_device();

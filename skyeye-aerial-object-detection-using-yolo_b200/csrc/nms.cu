@@ -137,41 +137,69 @@ __device__ __forceinline__ bool class_pass(const FilterParams& p, float col5) {
     return false;
 }
 
-// One thread per (image, box). Emits sort keys of surviving rows; order-free (the key is total).
-__global__ void nms_filter_kernel(const FilterParams p, unsigned long long* __restrict__ keys, unsigned int* __restrict__ total,
-                                  int* __restrict__ count) {
+// One thread per (image, box).  Every thread writes its own key slot(s): the sort key of a surviving
+// row or the all-ones sentinel (sorts last), so no position atomics are needed; the per-image counts
+// are warp-aggregated (one atomic per warp when the warp sits inside one image).
+__global__ void nms_filter_kernel(const FilterParams p, unsigned long long* __restrict__ keys, int* __restrict__ count) {
     const long nbox = (long)p.B * p.N;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nbox; i += (long)gridDim.x * blockDim.x) {
-        const int b = (int)(i / p.N), r = (int)(i % p.N);
-        const float* x = p.pred + i * p.no;
-        const float obj = x[4];
-        if (!(obj > p.conf)) continue;  // metrics.py:391,402
-        auto emit = [&](float score, int slot) {
-            const unsigned int pos = atomicAdd(total, 1u);
-            atomicAdd(count + b, 1);
-            keys[pos] = ((unsigned long long)b << (32 + KEY_SLOT_BITS)) | ((unsigned long long)desc_bits(score) << KEY_SLOT_BITS) |
-                        (unsigned long long)slot;
-        };
-        if (p.nc > 1 || (p.compat == 1 && p.nc == 1)) {
-            if (p.multi_label) {  // metrics.py:407-410: one row per (box, class) above the threshold
-                for (int j = 0; j < p.nc; ++j) {
-                    const float cp = x[5 + j];
-                    const float conf = p.compat ? __fmul_rn(cp, obj) : cp;
-                    if (conf > p.conf && class_pass(p, p.compat ? (float)j : cp)) emit(p.compat ? conf : obj, r * p.nc + j);
+    const long nround = (nbox + blockDim.x - 1) / blockDim.x * blockDim.x;  // whole warps stay in the loop together
+    const int per = p.multi_label ? p.nc : 1;
+    const int lane = threadIdx.x & 31;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nround; i += (long)gridDim.x * blockDim.x) {
+        const bool inb = i < nbox;
+        const int b = inb ? (int)(i / p.N) : -1;
+        int emitted = 0;
+        if (inb) {
+            const int r = (int)(i % p.N);
+            const float* x = p.pred + i * p.no;
+            const float obj = x[4];
+            unsigned long long* kout = keys + i * per;
+            const bool pass = obj > p.conf;  // metrics.py:391,402
+            auto key_of = [&](float score, int slot) {
+                return ((unsigned long long)b << (32 + KEY_SLOT_BITS)) | ((unsigned long long)desc_bits(score) << KEY_SLOT_BITS) |
+                       (unsigned long long)slot;
+            };
+            const unsigned long long none = ~0ULL;
+            if (p.nc > 1 || (p.compat == 1 && p.nc == 1)) {
+                if (p.multi_label) {  // metrics.py:407-410: one row per (box, class) above the threshold
+                    for (int j = 0; j < p.nc; ++j) {
+                        unsigned long long k = none;
+                        if (pass) {
+                            const float cp = x[5 + j];
+                            const float conf = p.compat ? __fmul_rn(cp, obj) : cp;
+                            if (conf > p.conf && class_pass(p, p.compat ? (float)j : cp)) { k = key_of(p.compat ? conf : obj, r * p.nc + j); ++emitted; }
+                        }
+                        kout[j] = k;
+                    }
+                } else {  // metrics.py:411-414: best class (first maximum)
+                    unsigned long long k = none;
+                    if (pass) {
+                        float best = x[5];
+                        int bj = 0;
+                        if (p.compat) best = __fmul_rn(best, obj);
+                        for (int j = 1; j < p.nc; ++j) {
+                            float cp = x[5 + j];
+                            if (p.compat) cp = __fmul_rn(cp, obj);
+                            if (cp > best) { best = cp; bj = j; }
+                        }
+                        if (best > p.conf && class_pass(p, p.compat ? (float)bj : best)) { k = key_of(p.compat ? best : obj, r * p.nc + bj); ++emitted; }
+                    }
+                    kout[0] = k;
                 }
-            } else {  // metrics.py:411-414: best class (first maximum)
-                float best = x[5];
-                int bj = 0;
-                if (p.compat) best = __fmul_rn(best, obj);
-                for (int j = 1; j < p.nc; ++j) {
-                    float cp = x[5 + j];
-                    if (p.compat) cp = __fmul_rn(cp, obj);
-                    if (cp > best) { best = cp; bj = j; }
-                }
-                if (best > p.conf && class_pass(p, p.compat ? (float)bj : best)) emit(p.compat ? best : obj, r * p.nc + bj);
+            } else {  // nc == 1 (metrics.py:415-419): row [cx,cy,w,h,obj,0]; nc == 0 in fixed mode
+                unsigned long long k = none;
+                if (pass && class_pass(p, 0.0f)) { k = key_of(obj, r); ++emitted; }
+                kout[0] = k;
             }
-        } else {  // nc == 1 (metrics.py:415-419): row [cx,cy,w,h,obj,0]; nc == 0 in fixed mode
-            if (class_pass(p, 0.0f)) emit(obj, r);
+        }
+        const int b0 = __shfl_sync(0xffffffffu, b, 0);
+        if (__all_sync(0xffffffffu, b == b0)) {
+            int tot = emitted;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            if (lane == 0 && tot > 0 && b0 >= 0) atomicAdd(count + b0, tot);
+        } else if (emitted > 0) {
+            atomicAdd(count + b, emitted);
         }
     }
 }
@@ -364,7 +392,6 @@ extern "C" int skb_nms_batched_f32(const float* pred, int32_t b, int32_t n, int3
     batched_layout(b, n, nc, multi_label, workspace, &ws);
     const size_t cap = (size_t)b * n * (multi_label ? nc : 1);
     cudaStream_t st = (cudaStream_t)stream;
-    SKB_CUDA(cudaMemsetAsync(ws.keys_in, 0xFF, 8 * cap, st));
     SKB_CUDA(cudaMemsetAsync(ws.total, 0, sizeof(int) * (b + 1), st));
     FilterParams fp;
     memset(&fp, 0, sizeof(fp));
@@ -374,7 +401,7 @@ extern "C" int skb_nms_batched_f32(const float* pred, int32_t b, int32_t n, int3
     const long nbox = (long)b * n;
     long g = (nbox + 255) / 256;
     const long gcap = (long)num_sms() * 16;
-    nms_filter_kernel<<<(int)(g > gcap ? gcap : g), 256, 0, st>>>(fp, ws.keys_in, ws.total, ws.count);
+    nms_filter_kernel<<<(int)(g > gcap ? gcap : g), 256, 0, st>>>(fp, ws.keys_in, ws.count);
     SKB_LAUNCH_CHECK();
     int img_bits = 1;
     while ((1 << img_bits) < b) ++img_bits;

@@ -20,7 +20,7 @@ CSRC = os.path.join(_PKG, "csrc")
 INCLUDE = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_HERE, "libskyeye_b200.so")
 
-SKB_BF16, SKB_F32 = 0, 1
+SKB_BF16, SKB_F32, SKB_U8 = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_RELU = 0, 1, 2
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -85,6 +85,9 @@ _SIGNATURES = {
     "skb_debug_conv_trace": (c_int32, [c_void_p]),
     "skb_focus_nchw_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, POINTER(skb_view), c_void_p]),
     "skb_focus_nchw_u8": (c_int32, [c_void_p, c_int32, c_int32, c_int32, POINTER(skb_view), c_void_p]),
+    "skb_focus_conv_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "skb_focus_conv_bf16": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, POINTER(skb_view),
+                                      c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
     "skb_maxpool5_bf16": (c_int32, [POINTER(skb_view), POINTER(skb_view), c_void_p]),
     "skb_cbam_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "skb_cbam_bf16": (c_int32, [POINTER(skb_view), c_void_p, c_void_p, c_int32, c_void_p, POINTER(skb_view),

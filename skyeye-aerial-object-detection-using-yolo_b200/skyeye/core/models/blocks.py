@@ -124,7 +124,16 @@ class FocusBlock(nn.Module):
         self.conv = ConvolutionBlock(in_channels * 4, out_channels, kernel_size, stride)
 
     def lower_image(self, plan: Plan, img_holder, n, h, w, name="focus") -> View:
-        cpad = 64 if self.conv.out_channels % 64 == 0 else 32
-        f = plan.buf(n, h // 2, w // 2, cpad)
-        plan.add(name + ".s2d", lambda s: L.E.focus(img_holder[0], f, s), "focus", 0.0, 3.0 * n * h * w * 4 + 2.0 * n * (h // 2) * (w // 2) * cpad)
-        return self.conv.lower(plan, f, name=name + ".conv")
+        c = self.conv
+        if c.kernel_size != 3 or c.stride != 1:
+            raise NotImplementedError("FocusBlock is lowered for the k3 s1 conv on the path (backbone.py:47)")
+        wf, bf = PackedConv.fold_bn(c.conv.weight, c.bn.weight, c.bn.bias, c.bn.running_mean, c.bn.running_var, c.bn.eps)
+        pw = L.E.PackedFocusConv(wf, bf, plan.device)
+        out = plan.buf(n, h // 2, w // 2, c.out_channels)
+        ws = plan.ws(L.E.N.lib().skb_focus_conv_workspace_bytes(n, h, w))
+        plan.keep.append(pw)
+        ho, wo = h // 2, w // 2
+        flops = 2.0 * n * ho * wo * c.out_channels * 9 * 12
+        nbytes = 3.0 * n * h * w + 2.0 * (2.0 * n * ho * (wo + 4) * 16) + 2.0 * n * ho * wo * c.out_channels  # uint8 image
+        plan.add(name, lambda s: L.E.focus_conv(img_holder[0], pw, out, ws, ACT_SILU, s), "conv", flops, nbytes, 2)
+        return out

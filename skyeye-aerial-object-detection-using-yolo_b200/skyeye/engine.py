@@ -117,6 +117,33 @@ class PackedConv:
         return out
 
 
+class PackedFocusConv:
+    """FocusBlock conv weights [cout, 12, 3, 3] in the row-tap layout of skb_focus_conv_bf16:
+    bf16 [cout_pad][ky 3][kx slot 4][channel 16]; slot 3 and channels 12..15 are zero."""
+
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], device="cuda"):
+        w = weight.detach().float().cpu()
+        cout, cin, kh, kw = w.shape
+        assert (cin, kh, kw) == (12, 3, 3), w.shape
+        self.cout, self.cout_pad = cout, round_cout(cout)
+        wp = torch.zeros((self.cout_pad, 3, 4, 16), dtype=torch.float32)
+        wp[:cout, :, :3, :12] = w.permute(0, 2, 3, 1)
+        self.w = wp.reshape(self.cout_pad, 192).to(device=device, dtype=torch.bfloat16).contiguous()
+        b = torch.zeros(self.cout_pad, dtype=torch.float32)
+        if bias is not None:
+            b[:cout] = bias.detach().float().cpu()
+        self.b = b.to(device)
+
+
+def focus_conv(img: torch.Tensor, pw: PackedFocusConv, y: View, ws: torch.Tensor, act: int = ACT_SILU, stream=None) -> None:
+    """FocusBlock.forward on an fp32 (already /255) or uint8 NCHW image: one native call."""
+    assert img.dtype in (torch.float32, torch.uint8) and img.is_contiguous() and img.dim() == 4 and img.shape[1] == 3
+    n, _, h, w = img.shape
+    N.check(N.lib().skb_focus_conv_bf16(img.data_ptr(), SKB_F32 if img.dtype == torch.float32 else N.SKB_U8, n, h, w,
+                                        pw.w.data_ptr(), pw.b.data_ptr(), y.ref, pw.cout_pad, act, ws.data_ptr(), ws.numel(),
+                                        _stream_ptr() if stream is None else stream), "skb_focus_conv_bf16")
+
+
 # ----------------------------------------------------------------------------------------------
 # eager op wrappers (one native call each)
 # ----------------------------------------------------------------------------------------------

@@ -75,6 +75,9 @@ CASES = [
     (1, 16, 16, 256, 45, 1, 1),       # detection head: Cout 45 -> padded, fp32 out
     (1, 6, 6, 2048, 1024, 1, 1),      # SPP cv2 shape class
     (1, 24, 40, 64, 192, 1, 1),       # non-square, Cout multiple of 64 only
+    (2, 32, 48, 16, 64, 3, 1),        # BK = 16 path (Focus conv: 12 channels padded to 16, SWIZZLE_32B)
+    (1, 16, 16, 16, 32, 3, 1),        # BK = 16, BN = 32 (skyeye_s stem)
+    (1, 16, 16, 48, 64, 1, 1),        # Cin % 32 != 0 -> BK = 16, three K chunks
 ]
 
 
@@ -147,9 +150,9 @@ def test_conv_large_layer_matches_sampled_reference():
 
 def test_conv_rejects_bad_arguments_loudly():
     from skyeye import engine as E
-    x = E.new_buffer(1, 8, 8, 48)  # Cin not a multiple of 32
+    x = E.new_buffer(1, 8, 8, 40)  # Cin not a multiple of 16
     with pytest.raises(AssertionError):
         E.conv2d(x, E.PackedConv(torch.zeros(64, 64, 1, 1), None), E.new_buffer(1, 8, 8, 64))
-    pw = E.PackedConv(torch.zeros(64, 48, 1, 1), None)
-    with pytest.raises(RuntimeError, match="multiple of 32"):
+    pw = E.PackedConv(torch.zeros(64, 40, 1, 1), None)
+    with pytest.raises(RuntimeError, match="multiple of 16"):
         E.conv2d(x, pw, E.new_buffer(1, 8, 8, 64))

@@ -31,6 +31,35 @@ def test_focus_space_to_depth_bit_exact():
     assert bool((got[:, 12:] == 0).all())
 
 
+@pytest.mark.parametrize("shape,cout,u8", [((2, 3, 32, 48), 64, False), ((1, 3, 64, 40), 32, True), ((3, 3, 24, 264), 64, True),
+                                           ((1, 3, 16, 16), 128, False)])
+def test_focus_block_fused_matches_oracle(shape, cout, u8):
+    """Whole FocusBlock (blocks.py:170-182) through skb_focus_conv_bf16: padded space-to-depth + the
+    3x3 conv over sliding 128-byte windows.  Reference = conv2d over the concatenated strided slices
+    with the same bf16-rounded operands (fp32 accumulate); includes the left/right/top/bottom borders
+    and ragged tiles (264 / 2 = 132 pixels = one full 128-pixel tile + 4)."""
+    from skyeye import engine as E
+    n, _, h, w = shape
+    if u8:
+        img8 = torch.from_numpy(cases.rng("focus_u8", shape).integers(0, 256, shape, dtype=np.uint8))
+        x = img8.float() / 255.0
+        dev_img = img8.cuda()
+    else:
+        x = cases.image(shape)
+        dev_img = x.cuda()
+    wt = bf16r(randn(("focus_w", cout), (cout, 12, 3, 3), (2.0 / 108) ** 0.5))
+    b = randn(("focus_b", cout), (cout,), 0.1)
+    pw = E.PackedFocusConv(wt, b)
+    y = E.new_buffer(n, h // 2, w // 2, cout)
+    y.t.fill_(7.0)
+    ws = E.workspace(E.N.lib().skb_focus_conv_workspace_bytes(n, h, w))
+    E.focus_conv(dev_img, pw, y, ws)
+    torch.cuda.synchronize()
+    s2d = bf16r(torch.cat([x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]], 1))
+    ref = F.silu(F.conv2d(s2d, wt, b, 1, 1))
+    assert rel_err(y.nchw(), ref) < TOL
+
+
 @pytest.mark.parametrize("shape", [(2, 64, 20, 20), (1, 256, 7, 9), (2, 32, 40, 40)])
 def test_maxpool5_cascade_equals_spp_pools_bit_exact(shape):
     from skyeye import engine as E
