@@ -3,16 +3,24 @@
 // which materialises the [B*h, N, N] weights (10.5 GB fp32 per image at N = 25600).
 //
 // One CTA = one (image, head, 128-query tile); it streams 64-key tiles of K and V:
-//   S  = Q K^T        tcgen05.mma SS, Q/K K-major SWIZZLE_128B tiles from TMA, S fp32 in TMEM (2 buffers)
+//   S  = Q K^T        tcgen05.mma with A = Q held in TMEM (copied there once), B = K tile (K-major,
+//                     SWIZZLE_128B, from TMA); S fp32 in TMEM, two buffers
 //   P  = exp2(S*c-m)  128 softmax threads (one query row each): tcgen05.ld -> online softmax with a
-//                     lazily updated reference max (rescale O only when the max grows by > 2^8) ->
-//                     bf16 P written to smem in the canonical K-major SWIZZLE_128B layout
-//   O += P V          tcgen05.mma SS, V consumed MN-major straight from its [key][d] TMA tile
+//                     lazily updated reference max (O is rescaled only when a row max grows by > 2^8) ->
+//                     bf16 P written back INTO the S buffer with tcgen05.st (no shared-memory round trip)
+//   O += P V          tcgen05.mma with A = P from TMEM, B = V consumed MN-major straight from its TMA tile
+// Shared memory therefore carries only the K/V stream (the smem port is shared by TMA writes and MMA
+// operand reads and was the co-bottleneck with P and Q staged there).  The softmax is MUFU-bound
+// (64 flop per exponential at head_dim 64), so ATT_POLY of every 64 exponentials are evaluated on the
+// FMA pipes instead (Cody-Waite split + degree-3 polynomial, rel. error 7.5e-5 << bf16), in packed
+// fp32x2 arithmetic.  MMAs of one CTA execute in issue order, which is what lets QK(j+2) reuse the
+// S/P buffer of tile j right after PV(j) has been issued.
 // The in_proj output [B, N, 3C] is read in place: one 3-D tensor map {channel, token, image} serves
 // Q, K and V (different channel coordinates), ragged N is TMA zero fill + a -inf mask on the last tile.
-// 2 CTAs are resident per SM (96 KB smem, 256 TMEM columns each) so one CTA's MUFU-bound softmax
-// overlaps the other's MMAs.  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = softmax/epilogue.
+// 2 CTAs are resident per SM (81 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the
+// other's MMAs.  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = softmax/epilogue.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -21,9 +29,9 @@ namespace skb {
 constexpr int ATT_BQ = 128, ATT_BKV = 64, ATT_D = 64, ATT_KVS = 4;
 constexpr int ATT_Q_BYTES = ATT_BQ * ATT_D * 2;     // 16 KB
 constexpr int ATT_KV_BYTES = ATT_BKV * ATT_D * 2;   // 8 KB
-constexpr int ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;   // 16 KB
-constexpr int ATT_SMEM = ATT_Q_BYTES + 2 * ATT_KVS * ATT_KV_BYTES + ATT_P_BYTES + 1024 + 256;
-constexpr uint32_t ATT_TMEM_COLS = 256;             // S0 [0,64) S1 [64,128) O [128,192)
+constexpr int ATT_SMEM = ATT_Q_BYTES + 2 * ATT_KVS * ATT_KV_BYTES + 1024 + 256;
+constexpr uint32_t ATT_TMEM_COLS = 256;             // S0/P0 [0,64) S1/P1 [64,128) O [128,192) Q [192,224)
+constexpr int ATT_POLY_DEFAULT = 8;                 // exponentials per 64 evaluated on the FMA pipes (0, 8, 16, 24, 32)
 
 struct AttnParams {
     int N, heads, C, T;
@@ -32,6 +40,40 @@ struct AttnParams {
     long out_pitch;
 };
 
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ float2 fadd2_rm(float2 a, float2 b) {  // round toward -inf
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rm.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;}" : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+// 2^x for x <= ~100 on the FMA / ALU pipes: n = floor(x) from the mantissa of x + 1.5*2^23 (round down),
+// f = x - n in [0,1), 2^f by a degree-3 minimax polynomial (max rel. error 7.5e-5), 2^n by adding n to
+// the exponent field.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+    x.x = fmaxf(x.x, -126.0f);
+    x.y = fmaxf(x.y, -126.0f);
+    const float2 y = fadd2_rm(x, make_float2(12582912.0f, 12582912.0f));
+    const float2 fl = fadd2(y, make_float2(-12582912.0f, -12582912.0f));
+    const float2 f = ffma2(fl, make_float2(-1.0f, -1.0f), x);
+    float2 pz = ffma2(f, make_float2(0.0780244768f, 0.0780244768f), make_float2(0.2260672152f, 0.2260672152f));
+    pz = ffma2(pz, f, make_float2(0.6958335042f, 0.6958335042f));
+    pz = ffma2(pz, f, make_float2(0.9999251962f, 0.9999251962f));
+    float2 r;
+    r.x = __int_as_float(__float_as_int(pz.x) + (__float_as_int(y.x) << 23));
+    r.y = __int_as_float(__float_as_int(pz.y) + (__float_as_int(y.y) << 23));
+    return r;
+}
+
+template <int ATT_POLY>
 __global__ void __launch_bounds__(192, 2)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -40,18 +82,16 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t sQ = base;
     const uint32_t sK0 = sQ + ATT_Q_BYTES;
     const uint32_t sV0 = sK0 + ATT_KVS * ATT_KV_BYTES;
-    const uint32_t sP = sV0 + ATT_KVS * ATT_KV_BYTES;
-    const uint32_t bar0 = sP + ATT_P_BYTES;
+    const uint32_t bar0 = sV0 + ATT_KVS * ATT_KV_BYTES;
     const uint32_t q_full = bar0;
-    auto kv_full = [&](int s) { return bar0 + 8u * (1 + s); };
-    auto kv_empty = [&](int s) { return bar0 + 8u * (1 + ATT_KVS + s); };
-    auto s_full = [&](int s) { return bar0 + 8u * (1 + 2 * ATT_KVS + s); };
-    auto s_empty = [&](int s) { return bar0 + 8u * (3 + 2 * ATT_KVS + s); };
-    const uint32_t p_full = bar0 + 8u * (5 + 2 * ATT_KVS);
-    const uint32_t pv_done = bar0 + 8u * (6 + 2 * ATT_KVS);
+    const uint32_t q_ready = bar0 + 8u;
+    auto kv_full = [&](int s) { return bar0 + 8u * (2 + s); };
+    auto kv_empty = [&](int s) { return bar0 + 8u * (2 + ATT_KVS + s); };
+    auto s_full = [&](int s) { return bar0 + 8u * (2 + 2 * ATT_KVS + s); };
+    auto p_full = [&](int s) { return bar0 + 8u * (4 + 2 * ATT_KVS + s); };
+    const uint32_t o_done = bar0 + 8u * (6 + 2 * ATT_KVS);
     const uint32_t slot = bar0 + 8u * (7 + 2 * ATT_KVS);
     volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - raw));
-    uint8_t* sP_ptr = smem_raw + (sP - raw);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
@@ -64,10 +104,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(q_full, 1);
+            mbar_init(q_ready, 4);
             for (int s = 0; s < ATT_KVS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-            for (int s = 0; s < 2; ++s) { mbar_init(s_full(s), 1); mbar_init(s_empty(s), 4); }
-            mbar_init(p_full, 4);
-            mbar_init(pv_done, 1);
+            for (int s = 0; s < 2; ++s) { mbar_init(s_full(s), 1); mbar_init(p_full(s), 4); }
+            mbar_init(o_done, 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -78,6 +118,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tc_fence_after();
     const uint32_t tmem = *slot_ptr;
     const uint32_t tmem_O = tmem + 128;
+    const uint32_t tmem_Q = tmem + 192;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -95,47 +136,62 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BQ, ATT_BKV, 0, 0);  // A = Q (K-major), B = K (K-major)
-        constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BQ, ATT_D, 0, 1);    // A = P (K-major), B = V (MN-major)
+        constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BQ, ATT_BKV, 0, 0);  // A = Q (TMEM), B = K (K-major)
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BQ, ATT_D, 0, 1);    // A = P (TMEM), B = V (MN-major)
         auto issue_qk = [&](int j) {
             const int s = j % ATT_KVS, sb = j & 1;
             mbar_wait(kv_full(s), (uint32_t)(j / ATT_KVS) & 1u);
-            mbar_wait(s_empty(sb), ((uint32_t)(j >> 1) & 1u) ^ 1u);
             tc_fence_after();
             if (lane == 0) {
-                const uint64_t ad = umma_desc(sQ, 16, 1024, UMMA_SW128);
                 const uint64_t bd = umma_desc(sK0 + s * ATT_KV_BYTES, 16, 1024, UMMA_SW128);
 #pragma unroll
-                for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(tmem + sb * ATT_BKV, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_qk, k > 0);
+                for (int k = 0; k < ATT_D / 16; ++k)  // 16 bf16 of A = 8 TMEM columns
+                    umma_bf16_ts(tmem + sb * ATT_BKV, tmem_Q + k * 8, bd + (uint64_t)(k * 2), idesc_qk, k > 0);
                 umma_commit(s_full(sb));
             }
             __syncwarp();
         };
-        mbar_wait(q_full, 0);
+        mbar_wait(q_ready, 0);
+        tc_fence_after();
         issue_qk(0);
+        if (T > 1) issue_qk(1);
         for (int j = 0; j < T; ++j) {
-            if (j + 1 < T) issue_qk(j + 1);
-            const int s = j % ATT_KVS;
-            mbar_wait(p_full, (uint32_t)j & 1u);
+            const int s = j % ATT_KVS, sb = j & 1;
+            mbar_wait(p_full(sb), (uint32_t)(j >> 1) & 1u);
             tc_fence_after();
             if (lane == 0) {
-                const uint64_t ad = umma_desc(sP, 16, 1024, UMMA_SW128);
                 // V tile [64 keys][64 d]: MN-major, 128-byte rows, 8-row groups 1024 B apart, 16 keys per MMA = 2048 B
                 const uint64_t bd = umma_desc(sV0 + s * ATT_KV_BYTES, 1024, 1024, UMMA_SW128);
 #pragma unroll
                 for (int k = 0; k < ATT_BKV / 16; ++k)
-                    umma_bf16_ss(tmem_O, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 128), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+                    umma_bf16_ts(tmem_O, tmem + sb * ATT_BKV + k * 8, bd + (uint64_t)(k * 128), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
                 umma_commit(kv_empty(s));
-                umma_commit(pv_done);
+                umma_commit(o_done);
             }
             __syncwarp();
+            if (j + 2 < T) issue_qk(j + 2);  // reuses S/P buffer sb: ordered behind PV(j) by in-order MMA execution
         }
     } else {
         // ===================== softmax + epilogue: thread <-> query row =====================
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        {   // Q tile (K-major SWIZZLE_128B rows in smem) -> TMEM columns [192,224): A operand of every QK MMA
+            mbar_wait(q_full, 0);
+            uint32_t qr[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 u = lds128(sQ + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4));
+                qr[4 * c + 0] = u.x; qr[4 * c + 1] = u.y; qr[4 * c + 2] = u.z; qr[4 * c + 3] = u.w;
+            }
+            tmem_st32(tmem_Q + lane_addr, qr);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q_ready);
+        }
         float m_ref = -INFINITY, l = 0.f;
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
         for (int j = 0; j < T; ++j) {
             const int sb = j & 1;
             mbar_wait(s_full(sb), (uint32_t)(j >> 1) & 1u);
@@ -148,17 +204,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 tmem_ld32(tmem + lane_addr + sb * ATT_BKV + 32, hi);
             }
             tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_empty(sb));
             // row max of the raw scores (keys beyond N masked on the ragged last tile)
-            float mx = -INFINITY;
             const int kbase = j * ATT_BKV;
             if (kbase + ATT_BKV > p.N) {
 #pragma unroll
                 for (int i = 0; i < 64; ++i)
                     if (kbase + i >= p.N) sv[i] = 0xff800000u;  // -inf
             }
+            float mx;
             {   // 8 independent chains instead of one 64-deep dependent FMNMX chain
                 float m8[8];
 #pragma unroll
@@ -172,8 +225,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             const bool need = mx > m_ref + 8.0f;
             const bool any = __any_sync(0xffffffffu, need);
             const float m_new = need ? mx : m_ref;
-            if (j > 0) mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);  // P buffer free, O quiescent
             if (any && j > 0) {
+                mbar_wait(o_done, (uint32_t)(j - 1) & 1u);  // PV(j-1) complete: O quiescent (PV(j) waits for our P)
                 tc_fence_after();
                 const float alpha = need ? exp2f(m_ref - m_new) : 1.0f;
                 l *= alpha;
@@ -189,29 +242,34 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 tmem_st_wait();
             }
             m_ref = m_new;
-            float sum8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            uint8_t* prow = sP_ptr + row * 128;
+            const float2 nm2 = make_float2(-m_ref, -m_ref);
+            float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+            uint32_t pk[32];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float e[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    e[i] = ex2_approx(fmaf(__uint_as_float(sv[c * 8 + i]), p.scale_log2, -m_ref));  // one FFMA + one MUFU
-                    sum8[i] += e[i];
+            for (int i = 0; i < 32; ++i) {  // pair i = keys 2i, 2i+1; every (64 / ATT_POLY)-th pair runs on the FMA pipes
+                const float2 x = ffma2(make_float2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sc2, nm2);
+                float2 e;
+                // pairs on the FMA pipes: POLY/2 of the 32 pairs, spread evenly (i*POLY/64 increments)
+                if (ATT_POLY > 0 && ((i + 1) * ATT_POLY / 64) != (i * ATT_POLY / 64)) {
+                    e = exp2_poly2(x);
+                } else {
+                    e.x = ex2_approx(x.x);
+                    e.y = ex2_approx(x.y);
                 }
-                uint4 u;
-                u.x = pack_bf16x2(e[0], e[1]); u.y = pack_bf16x2(e[2], e[3]);
-                u.z = pack_bf16x2(e[4], e[5]); u.w = pack_bf16x2(e[6], e[7]);
-                *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = u;  // SWIZZLE_128B: 16B chunk ^= row % 8
+                acc[i & 3] = fadd2(acc[i & 3], e);
+                pk[i] = pack_bf16x2(e.x, e.y);
             }
-            l += ((sum8[0] + sum8[1]) + (sum8[2] + sum8[3])) + ((sum8[4] + sum8[5]) + (sum8[6] + sum8[7]));
-            fence_proxy_async_smem();
+            // P (bf16, K-major: lane = query row, column c holds keys 2c, 2c+1) over the first half of S
+            tmem_st32(tmem + lane_addr + sb * ATT_BKV, pk);
+            const float2 a01 = fadd2(fadd2(acc[0], acc[1]), fadd2(acc[2], acc[3]));
+            l += a01.x + a01.y;
+            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
+            if (lane == 0) mbar_arrive(p_full(sb));
         }
         // ---- epilogue: O / l -> bf16 ----
-        mbar_wait(pv_done, (uint32_t)(T - 1) & 1u);
+        mbar_wait(o_done, (uint32_t)(T - 1) & 1u);
         tc_fence_after();
         const float inv = 1.0f / l;
         const int token = qt * ATT_BQ + row;
@@ -267,13 +325,26 @@ extern "C" int skb_flash_attn_bf16(const skb_view* qkv, const skb_view* o, int32
     p.N = N; p.heads = heads; p.C = C; p.T = (N + ATT_BKV - 1) / ATT_BKV;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.out = (__nv_bfloat16*)o->ptr; p.out_pitch = o->pitch;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        attr_set = true;
+    static int poly = -1;
+    if (poly < 0) {  // tuning knob (not part of the ABI): SKB_ATT_POLY in {0, 8, 16, 24, 32}
+        const char* e = getenv("SKB_ATT_POLY");
+        poly = e ? atoi(e) : ATT_POLY_DEFAULT;
+        if (poly != 0 && poly != 8 && poly != 16 && poly != 24 && poly != 32) poly = ATT_POLY_DEFAULT;
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     }
     dim3 grid((N + ATT_BQ - 1) / ATT_BQ, heads, B);
-    flash_attn_kernel<<<grid, 192, ATT_SMEM, (cudaStream_t)stream>>>(tmQ, tmKV, p);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (poly) {
+        case 0: flash_attn_kernel<0><<<grid, 192, ATT_SMEM, st>>>(tmQ, tmKV, p); break;
+        case 8: flash_attn_kernel<8><<<grid, 192, ATT_SMEM, st>>>(tmQ, tmKV, p); break;
+        case 24: flash_attn_kernel<24><<<grid, 192, ATT_SMEM, st>>>(tmQ, tmKV, p); break;
+        case 32: flash_attn_kernel<32><<<grid, 192, ATT_SMEM, st>>>(tmQ, tmKV, p); break;
+        default: flash_attn_kernel<16><<<grid, 192, ATT_SMEM, st>>>(tmQ, tmKV, p); break;
+    }
     SKB_LAUNCH_CHECK();
     return SKB_OK;
 }
