@@ -120,7 +120,8 @@ int skb_layernorm_bf16(const skb_view* x, const float* gamma, const float* beta,
 int skb_flash_attn_bf16(const skb_view* qkv, const skb_view* o, int32_t heads, float scale, void* stream);
 
 /* ---- decode (DetectionHead.process_detections, detector.py:88-145) -----------------------------
- * raw[l]: fp32 view [B,h_l,w_l,>=na*no] (channel = a*no + o, the 1x1 head conv output).
+ * raw[l]: fp32 view [B,h_l,w_l,>=na*no] (channel = a*no + o, the 1x1 head conv output); 16-byte aligned,
+ *   pitch a multiple of 4 and >= na*no rounded up to 4 (rows are staged with 16-byte loads).
  * det: fp32 [B, sum_l na*h_l*w_l, no], rows ordered (level, anchor, y, x).
  * raw_out[l] (nullable): fp32 [B,na,h_l,w_l,no] = the reference's raw_outputs (detector.py:81-82).
  * anchors: host fp32 [levels][na][2] in pixels (multiplied by stride again, quirk X16). */

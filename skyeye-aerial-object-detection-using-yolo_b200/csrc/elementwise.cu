@@ -285,38 +285,62 @@ __device__ __forceinline__ void bilin_load8(const __nv_bfloat16* __restrict__ t,
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = w00 * a[j] + w01 * bb[j] + w10 * cc[j] + w11 * d[j];
 }
-// scores s[n,g,y,x] = scale * sum_{c in head g} q * bilinear(k). one warp per pixel
-__global__ void cla_score_kernel(const __nv_bfloat16* __restrict__ q, long qpitch, const __nv_bfloat16* __restrict__ k, long kpitch,
-                                 int N, int H, int W, int Hk, int Wk, int Cq, int heads, float scale, float* __restrict__ s) {
-    const int lane = threadIdx.x & 31;
-    const long npix = (long)N * H * W;
-    const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
-    const long nw = ((long)gridDim.x * blockDim.x) >> 5;
-    const int cph = Cq / heads;
-    for (long p = wid; p < npix; p += nw) {
-        const int px = (int)(p % W);
-        const int py = (int)((p / W) % H);
-        const int n = (int)(p / ((long)W * H));
-        const Bilin b = bilin_coords(py, px, H, W, Hk, Wk);
+// scores s[n,g,y,x] = scale * sum_{c in head g} q * bilinear(k).  One CTA per image row (n, y): warps
+// stride over x two pixels at a time (10 independent 16-byte loads in flight per lane), a head is a
+// lane-aligned group of cph/8 lanes (segmented shuffle reduce), and the row's scores are staged in
+// shared memory so the global writes are coalesced.
+__device__ __forceinline__ void bilin_y(int y, int H, int Hk, int& y0, int& y1, float& ly) {
+    const float sy = fmaxf(((float)y + 0.5f) * ((float)Hk / (float)H) - 0.5f, 0.f);
+    y0 = (int)sy; y1 = min(y0 + 1, Hk - 1); ly = sy - (float)y0;
+}
+__global__ void __launch_bounds__(256)
+cla_score_kernel(const __nv_bfloat16* __restrict__ q, long qpitch, const __nv_bfloat16* __restrict__ k, long kpitch,
+                 int N, int H, int W, int Hk, int Wk, int Cq, int heads, float scale, float* __restrict__ s) {
+    extern __shared__ float srow[];  // [heads][W]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int n = blockIdx.x / H, py = blockIdx.x - n * H;
+    const int cph = Cq / heads, lph = cph >> 3;  // lanes per head (power of two, host-checked)
+    Bilin b0, b1;
+    bilin_y(py, H, Hk, b0.y0, b0.y1, b0.ly);
+    b1.y0 = b0.y0; b1.y1 = b0.y1; b1.ly = b0.ly;
+    const float rx = (float)Wk / (float)W;
+    for (int x0 = warp; x0 < W; x0 += 2 * nwarp) {
+        const int x1 = x0 + nwarp;
+        const bool two = x1 < W;
+        {
+            const float sx = fmaxf(((float)x0 + 0.5f) * rx - 0.5f, 0.f);
+            b0.x0 = (int)sx; b0.x1 = min(b0.x0 + 1, Wk - 1); b0.lx = sx - (float)b0.x0;
+            const float sx1 = fmaxf(((float)(two ? x1 : x0) + 0.5f) * rx - 0.5f, 0.f);
+            b1.x0 = (int)sx1; b1.x1 = min(b1.x0 + 1, Wk - 1); b1.lx = sx1 - (float)b1.x0;
+        }
+        const long p0 = ((long)n * H + py) * W + x0, p1 = two ? p0 + nwarp : p0;
         for (int cbase = 0; cbase < Cq; cbase += 256) {
             const int c = cbase + lane * 8;
-            float part = 0.f;
-            int head = -1;
+            float part0 = 0.f, part1 = 0.f;
             if (c < Cq) {
-                float qv[8], kv[8];
-                unpack8(*reinterpret_cast<const uint4*>(q + p * qpitch + c), qv);
-                bilin_load8(k, kpitch, n, Hk, Wk, b, c, kv);
+                float q0[8], q1[8], k0[8], k1[8];
+                unpack8(*reinterpret_cast<const uint4*>(q + p0 * qpitch + c), q0);
+                unpack8(*reinterpret_cast<const uint4*>(q + p1 * qpitch + c), q1);
+                bilin_load8(k, kpitch, n, Hk, Wk, b0, c, k0);
+                bilin_load8(k, kpitch, n, Hk, Wk, b1, c, k1);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) part += qv[j] * kv[j];
-                head = c / cph;
+                for (int j = 0; j < 8; ++j) { part0 += q0[j] * k0[j]; part1 += q1[j] * k1[j]; }
             }
-            // host guarantees 256 % cph == 0: a head never straddles two 256-channel passes
-            const int h_lo = cbase / cph, h_hi = min(heads - 1, (min(Cq, cbase + 256) - 1) / cph);
-            for (int g = h_lo; g <= h_hi; ++g) {
-                const float v = warp_sum(head == g ? part : 0.f);
-                if (lane == 0) s[(((long)n * heads + g) * H + py) * W + px] = v * scale;
+            for (int o = lph >> 1; o > 0; o >>= 1) {
+                part0 += __shfl_xor_sync(0xffffffffu, part0, o);
+                part1 += __shfl_xor_sync(0xffffffffu, part1, o);
+            }
+            if (c < Cq && (lane & (lph - 1)) == 0) {
+                const int g = c / cph;
+                srow[g * W + x0] = part0 * scale;
+                if (two) srow[g * W + x1] = part1 * scale;
             }
         }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < heads * W; i += blockDim.x) {
+        const int g = i / W, x = i - g * W;
+        s[(((long)n * heads + g) * H + py) * W + x] = srow[i];
     }
 }
 // column softmax statistics over image rows: one thread per (n, g, x)
@@ -334,79 +358,107 @@ __global__ void cla_colstat_kernel(const float* __restrict__ s, int NG, int H, i
         st[i * 2 + 1] = 1.0f / sum;
     }
 }
-// o[n,y,x,c] = r2 * softmax_y(s)[head(c)] * bilinear(v)[c]. one warp per pixel
-__global__ void cla_apply_kernel(const float* __restrict__ s, const float* __restrict__ st, const __nv_bfloat16* __restrict__ v, long vpitch,
-                                 int N, int H, int W, int Hk, int Wk, int Cv, int heads, float r2, __nv_bfloat16* __restrict__ o, long opitch) {
-    const int lane = threadIdx.x & 31;
-    const long npix = (long)N * H * W;
-    const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
-    const long nw = ((long)gridDim.x * blockDim.x) >> 5;
+// o[n,y,x,c] = r2 * softmax_y(s)[head(c)] * bilinear(v)[c].  One CTA per image row: the row's attention
+// weights are computed once into shared memory, then warps stride over x two pixels at a time.
+__global__ void __launch_bounds__(256)
+cla_apply_kernel(const float* __restrict__ s, const float* __restrict__ st, const __nv_bfloat16* __restrict__ v, long vpitch,
+                 int N, int H, int W, int Hk, int Wk, int Cv, int heads, float r2, __nv_bfloat16* __restrict__ o, long opitch) {
+    extern __shared__ float arow[];  // [heads][W]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int n = blockIdx.x / H, py = blockIdx.x - n * H;
+    for (int i = threadIdx.x; i < heads * W; i += blockDim.x) {
+        const int g = i / W, x = i - g * W;
+        const long ng = (long)n * heads + g;
+        const float sc = s[(ng * H + py) * W + x];
+        const float2 ms = *reinterpret_cast<const float2*>(st + (ng * W + x) * 2);
+        arow[i] = r2 * expf(sc - ms.x) * ms.y;
+    }
+    __syncthreads();
     const int cph = Cv / heads;
-    for (long p = wid; p < npix; p += nw) {
-        const int px = (int)(p % W);
-        const int py = (int)((p / W) % H);
-        const int n = (int)(p / ((long)W * H));
-        const Bilin b = bilin_coords(py, px, H, W, Hk, Wk);
-        float a = 0.f;  // lane g (< heads) holds the attention weight of head g
-        if (lane < heads) {
-            const long ng = (long)n * heads + lane;
-            const float sc = s[(ng * H + py) * W + px];
-            const float2 ms = *reinterpret_cast<const float2*>(st + (ng * W + px) * 2);
-            a = r2 * expf(sc - ms.x) * ms.y;
+    Bilin b0, b1;
+    bilin_y(py, H, Hk, b0.y0, b0.y1, b0.ly);
+    b1.y0 = b0.y0; b1.y1 = b0.y1; b1.ly = b0.ly;
+    const float rx = (float)Wk / (float)W;
+    for (int x0 = warp; x0 < W; x0 += 2 * nwarp) {
+        const int x1 = x0 + nwarp;
+        const bool two = x1 < W;
+        {
+            const float sx = fmaxf(((float)x0 + 0.5f) * rx - 0.5f, 0.f);
+            b0.x0 = (int)sx; b0.x1 = min(b0.x0 + 1, Wk - 1); b0.lx = sx - (float)b0.x0;
+            const float sx1 = fmaxf(((float)(two ? x1 : x0) + 0.5f) * rx - 0.5f, 0.f);
+            b1.x0 = (int)sx1; b1.x1 = min(b1.x0 + 1, Wk - 1); b1.lx = sx1 - (float)b1.x0;
         }
+        const long p0 = ((long)n * H + py) * W + x0, p1 = p0 + nwarp;
         for (int c = lane * 8; c < Cv; c += 256) {
-            float vv[8];
-            bilin_load8(v, vpitch, n, Hk, Wk, b, c, vv);
-            const float w = __shfl_sync(0xffffffffu, a, c / cph);
+            float v0[8], v1[8];
+            bilin_load8(v, vpitch, n, Hk, Wk, b0, c, v0);
+            bilin_load8(v, vpitch, n, Hk, Wk, b1, c, v1);
+            const int g = c / cph;
+            const float w0 = arow[g * W + x0], w1 = arow[g * W + (two ? x1 : x0)];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) vv[j] *= w;
-            *reinterpret_cast<uint4*>(o + p * opitch + c) = pack8(vv);
+            for (int j = 0; j < 8; ++j) { v0[j] *= w0; v1[j] *= w1; }
+            *reinterpret_cast<uint4*>(o + p0 * opitch + c) = pack8(v0);
+            if (two) *reinterpret_cast<uint4*>(o + p1 * opitch + c) = pack8(v1);
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// LayerNorm over channels, one warp per token (C <= 2048, multiple of 8)
+// LayerNorm over channels: one warp per token, VPL 16-byte vectors per lane (C = 256 * VPL, or less
+// with idle lanes), TPI tokens in flight per warp so that 4 independent loads per lane are
+// outstanding (the one-token version was latency-bound at 1.5 TB/s).
 // ---------------------------------------------------------------------------------------------
-__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long xpitch, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, float eps, long ntok, int C, __nv_bfloat16* __restrict__ y, long ypitch) {
+template <int VPL, int TPI>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __nv_bfloat16* __restrict__ x, long xpitch, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, long ntok, int C, __nv_bfloat16* __restrict__ y, long ypitch) {
     const int lane = threadIdx.x & 31;
     const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
     const long nw = ((long)gridDim.x * blockDim.x) >> 5;
-    for (long t = wid; t < ntok; t += nw) {
-        float f[8][8];
-        float s = 0.f;
+    const float invC = 1.0f / (float)C;
+    for (long t0 = wid * TPI; t0 < ntok; t0 += nw * TPI) {
+        uint4 u[TPI][VPL];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = lane * 8 + i * 256;
-            if (c < C) {
-                unpack8(*reinterpret_cast<const uint4*>(x + t * xpitch + c), f[i]);
+        for (int k = 0; k < TPI; ++k)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) s += f[i][j];
+            for (int i = 0; i < VPL; ++i) {
+                const int c = lane * 8 + i * 256;
+                u[k][i] = (t0 + k < ntok && c < C) ? *reinterpret_cast<const uint4*>(x + (t0 + k) * xpitch + c) : make_uint4(0u, 0u, 0u, 0u);
             }
-        }
-        const float mean = warp_sum(s) / (float)C;
-        float v = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (lane * 8 + i * 256 < C) {
+        for (int k = 0; k < TPI; ++k) {
+            if (t0 + k >= ntok) break;
+            float f[VPL][8];
+            float s = 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; v += d * d; }
+            for (int i = 0; i < VPL; ++i) {
+                unpack8(u[k][i], f[i]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += f[i][j];  // lanes beyond C hold zeros
             }
-        }
-        const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
+            const float mean = warp_sum(s) * invC;
+            float v = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = lane * 8 + i * 256;
-            if (c < C) {
-                const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
-                const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
-                float o[8];
-                o[0] = (f[i][0] - mean) * rstd * g0.x + b0.x; o[1] = (f[i][1] - mean) * rstd * g0.y + b0.y;
-                o[2] = (f[i][2] - mean) * rstd * g0.z + b0.z; o[3] = (f[i][3] - mean) * rstd * g0.w + b0.w;
-                o[4] = (f[i][4] - mean) * rstd * g1.x + b1.x; o[5] = (f[i][5] - mean) * rstd * g1.y + b1.y;
-                o[6] = (f[i][6] - mean) * rstd * g1.z + b1.z; o[7] = (f[i][7] - mean) * rstd * g1.w + b1.w;
-                *reinterpret_cast<uint4*>(y + t * ypitch + c) = pack8(o);
+            for (int i = 0; i < VPL; ++i) {
+                if (lane * 8 + i * 256 < C) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; v += d * d; }
+                }
+            }
+            const float rstd = rsqrtf(warp_sum(v) * invC + eps);
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                const int c = lane * 8 + i * 256;
+                if (c < C) {
+                    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+                    float o[8];
+                    o[0] = (f[i][0] - mean) * rstd * g0.x + b0.x; o[1] = (f[i][1] - mean) * rstd * g0.y + b0.y;
+                    o[2] = (f[i][2] - mean) * rstd * g0.z + b0.z; o[3] = (f[i][3] - mean) * rstd * g0.w + b0.w;
+                    o[4] = (f[i][4] - mean) * rstd * g1.x + b1.x; o[5] = (f[i][5] - mean) * rstd * g1.y + b1.y;
+                    o[6] = (f[i][6] - mean) * rstd * g1.z + b1.z; o[7] = (f[i][7] - mean) * rstd * g1.w + b1.w;
+                    *reinterpret_cast<uint4*>(y + (t0 + k) * ypitch + c) = pack8(o);
+                }
             }
         }
     }
@@ -533,13 +585,15 @@ extern "C" int skb_cla_core_bf16(const skb_view* q, const skb_view* k, const skb
     st = (float*)(((uintptr_t)st + 15) & ~(uintptr_t)15);
     cudaStream_t cs = (cudaStream_t)stream;
     const long npix = (long)N * H * W;
-    cla_score_kernel<<<grid_for(npix, 8), 256, 0, cs>>>((const __nv_bfloat16*)q->ptr, q->pitch, (const __nv_bfloat16*)k->ptr, k->pitch, N, H, W,
-                                                       k->h, k->w, q->c, heads, scale, s);
+    const size_t row_sh = sizeof(float) * (size_t)heads * W;
+    SKB_REQUIRE(row_sh <= 48 * 1024, SKB_ERR_UNSUPPORTED, "cla: heads*W = %d too large for the row staging buffer", heads * W);
+    cla_score_kernel<<<N * H, 256, row_sh, cs>>>((const __nv_bfloat16*)q->ptr, q->pitch, (const __nv_bfloat16*)k->ptr, k->pitch, N, H, W,
+                                                 k->h, k->w, q->c, heads, scale, s);
     SKB_LAUNCH_CHECK();
     cla_colstat_kernel<<<grid_for((long)N * heads * W, 128), 128, 0, cs>>>(s, N * heads, H, W, st);
     SKB_LAUNCH_CHECK();
-    cla_apply_kernel<<<grid_for(npix, 8), 256, 0, cs>>>(s, st, (const __nv_bfloat16*)v->ptr, v->pitch, N, H, W, v->h, v->w, v->c, heads, r2,
-                                                       (__nv_bfloat16*)o->ptr, o->pitch);
+    cla_apply_kernel<<<N * H, 256, row_sh, cs>>>(s, st, (const __nv_bfloat16*)v->ptr, v->pitch, N, H, W, v->h, v->w, v->c, heads, r2,
+                                                 (__nv_bfloat16*)o->ptr, o->pitch);
     SKB_LAUNCH_CHECK();
     return SKB_OK;
 }
@@ -551,8 +605,18 @@ extern "C" int skb_layernorm_bf16(const skb_view* x, const float* gamma, const f
     SKB_REQUIRE(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c, SKB_ERR_ARG, "layernorm: shape mismatch");
     SKB_REQUIRE(x->c <= 2048, SKB_ERR_UNSUPPORTED, "layernorm: C=%d > 2048", x->c);
     const long ntok = (long)x->n * x->h * x->w;
-    layernorm_kernel<<<grid_for(ntok, 8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x->ptr, x->pitch, gamma, beta, eps, ntok, x->c,
-                                                                         (__nv_bfloat16*)y->ptr, y->pitch);
+    const __nv_bfloat16* xp = (const __nv_bfloat16*)x->ptr;
+    __nv_bfloat16* yp = (__nv_bfloat16*)y->ptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int C = x->c;
+    if (C <= 256)
+        layernorm_kernel<1, 4><<<grid_for(ntok, 32), 256, 0, st>>>(xp, x->pitch, gamma, beta, eps, ntok, C, yp, y->pitch);
+    else if (C <= 512)
+        layernorm_kernel<2, 2><<<grid_for(ntok, 16), 256, 0, st>>>(xp, x->pitch, gamma, beta, eps, ntok, C, yp, y->pitch);
+    else if (C <= 1024)
+        layernorm_kernel<4, 1><<<grid_for(ntok, 8), 256, 0, st>>>(xp, x->pitch, gamma, beta, eps, ntok, C, yp, y->pitch);
+    else
+        layernorm_kernel<8, 1><<<grid_for(ntok, 8), 256, 0, st>>>(xp, x->pitch, gamma, beta, eps, ntok, C, yp, y->pitch);
     SKB_LAUNCH_CHECK();
     return SKB_OK;
 }
