@@ -11,7 +11,8 @@
 // * B operand: weights [Cout_pad][taps*Cin] bf16 (BN folded), 2-D tensor map, same swizzle.
 // * Accumulators: fp32 in TMEM, double buffered (2 x BN columns) so the epilogue of tile i overlaps
 //   the MMAs of tile i+1.  Persistent CTAs, static tile schedule (Cout block fastest).
-// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = two epilogue
+// * Warp roles: warp 0 = TMA producer (activations), warp 10 = TMA producer (weights), warp 1 = MMA
+//   issuer (+TMEM alloc), warps 2..9 = two epilogue
 //   groups of 4 warps.  Group g drains TMEM accumulator stage g, i.e. tiles alternate between the
 //   groups and two epilogues are in flight while the MMAs of a third tile run.  Each warp owns its
 //   TMEM lane quarter (32 pixels) and walks the columns in 32-column pieces:
@@ -27,6 +28,8 @@
 //
 // Replaces ConvolutionBlock.forward (skyeye/core/models/blocks.py:36-38) and friends, see
 // include/skyeye_b200.h.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace skb {
@@ -78,10 +81,10 @@ struct ConvParams {
         if (p.trace && blockIdx.x == 0 && tr_n < 4096) { p.trace[(role) * 8192 + 2 * tr_n] = (ev); p.trace[(role) * 8192 + 2 * tr_n + 1] = clock64(); ++tr_n; } \
     } while (0)
 
-template <int BN, int BK>
+template <int BN, int BK, int NCTA>
 struct ConvCfg {
     static constexpr int A_BYTES = 128 * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = (BN / NCTA) * BK * 2;  // a CTA pair splits the weight tile: N/2 rows each
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int EPI_GROUPS = 2;       // two 4-warp epilogue groups, one per TMEM accumulator stage
     static constexpr int EPI_NB = 2;           // staging slots per group (sub-tiles)
@@ -93,9 +96,13 @@ struct ConvCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 512;
 };
 
-__device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& nb, int& w0, int& h0, int& n0) {
+// work item (one per CTA, or per CTA pair) -> n-block and this CTA's pixel box.  In a pair, CTA r takes
+// M tile 2*mp + r; a phantom tile past the end decodes to n0 >= B: its loads are zero fill, its stores clip.
+template <int NCTA>
+__device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int cta_rank, int& nb, int& w0, int& h0, int& n0) {
     int mt, iw, ih, in;
     fast_divmod(p.fd_nb, tile, mt, nb);
+    mt = mt * NCTA + cta_rank;
     fast_divmod(p.fd_tw, mt, mt, iw);
     fast_divmod(p.fd_th, mt, in, ih);
     w0 = iw * p.tw; h0 = ih * p.th; n0 = in * p.tn;
@@ -147,11 +154,19 @@ __device__ __forceinline__ void epi_chunk_f32(const uint32_t* v, uint32_t bias_a
     sts128(a16, o4);
 }
 
-template <int BN, int BK>
-__global__ void __launch_bounds__(320, 1)
+template <int BN, int BK, int NCTA>
+__global__ void __launch_bounds__(352, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const ConvParams p) {
-    using Cfg = ConvCfg<BN, BK>;
+    using Cfg = ConvCfg<BN, BK, NCTA>;
+    // NCTA == 2: the two CTAs of a cluster form a tcgen05 CTA pair.  One MMA (issued by the leader) computes
+    // a 256 x BN tile: each CTA stages ITS 128 pixels and HALF of the weight tile, so the shared-memory
+    // traffic per MMA cycle drops from 128*(128+BN)/BN to 128*(128+BN/2)/BN B/clk (192 -> 128 at BN = 256,
+    // 256 -> 192 at BN = 128) -- the smem port, not the tensor pipe, bounds the single-CTA kernel.
+    const int cta_rank = NCTA == 2 ? (int)cluster_ctarank() : 0;
+    const bool leader = cta_rank == 0;
+    const int work0 = NCTA == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // first work item of this CTA (pair)
+    const int wstride = NCTA == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     constexpr int STAGES = Cfg::STAGES;
     constexpr uint32_t SW = BK == 64 ? UMMA_SW128 : (BK == 32 ? UMMA_SW64 : UMMA_SW32);
     constexpr uint32_t SBO = 8 * BK * 2;  // bytes between 8-row groups
@@ -189,37 +204,55 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(tfull(s), 1);
-                mbar_init(tempty(s), 4);
+                mbar_init(tempty(s), 4 * NCTA);  // every epilogue warp of the pair arrives on the leader's barrier
             }
             for (int s = 0; s < Cfg::EPI_GROUPS * NB; ++s) mbar_init(res_full(s), 1);
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc(slot, Cfg::TMEM_COLS);
+        if (NCTA == 2) tmem_alloc_pair(slot, Cfg::TMEM_COLS);
+        else tmem_alloc(slot, Cfg::TMEM_COLS);
     }
     tc_fence_before();
-    __syncthreads();
+    if (NCTA == 2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *slot_ptr;
 
-    if (warp == 0) {
-        // ===================== TMA producer =====================
+    if (warp == 0 || warp == 10) {
+        // ===================== TMA producers =====================
+        // One cp.async.bulk.tensor costs its issuing thread ~300 cycles whatever the box size (measured:
+        // a 6 KB and a 32 KB k-iteration both took ~630 cycles with one thread issuing both loads), so the
+        // activation and the weight tile of a stage are issued by two threads in different warps.  Warp 0
+        // arms the stage's barrier with the total byte count and loads A, warp 10 loads B; B's bytes may
+        // complete first (a transiently negative tx-count), the phase cannot complete before the arm.
+        const bool loads_a = warp == 0;
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             int tr_n = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int tile = work0; tile < p.total_tiles; tile += wstride) {
                 int nb, w0, h0, n0;
-                decode_tile(p, tile, nb, w0, h0, n0);
+                decode_tile<NCTA>(p, tile, cta_rank, nb, w0, h0, n0);
                 for (int it = 0; it < p.k_iters; ++it) {
-                    const int tap = it / p.cchunks;
-                    const int cc = it - tap * p.cchunks;
                     mbar_wait(empty(stage), phase ^ 1);
-                    SKB_TR(0, it);
-                    mbar_expect_tx(full(stage), (uint32_t)(p.a_box_bytes + Cfg::B_BYTES));
-                    tma_load_5d(sA0 + stage * Cfg::A_BYTES, &tmA, full(stage), p.tap_coff[tap] + cc * BK,
-                                w0 + p.tap_dw[tap], p.tap_ph[tap], h0 + p.tap_dh[tap], n0);
-                    tma_load_2d(sB0 + stage * Cfg::B_BYTES, &tmB, full(stage), it * BK, nb * BN);
+                    // pair: both CTAs' bytes complete on the LEADER's full barrier (its single arrival carries the total)
+                    const uint32_t fb = NCTA == 2 ? mapa_shared(full(stage), 0) : full(stage);
+                    if (loads_a) {
+                        const int tap = it / p.cchunks;
+                        const int cc = it - tap * p.cchunks;
+                        SKB_TR(0, it);
+                        if (leader) mbar_expect_tx(full(stage), (uint32_t)NCTA * (uint32_t)(p.a_box_bytes + Cfg::B_BYTES));
+                        if (NCTA == 2)
+                            tma_load_5d_pair(sA0 + stage * Cfg::A_BYTES, &tmA, fb, p.tap_coff[tap] + cc * BK,
+                                             w0 + p.tap_dw[tap], p.tap_ph[tap], h0 + p.tap_dh[tap], n0);
+                        else
+                            tma_load_5d(sA0 + stage * Cfg::A_BYTES, &tmA, fb, p.tap_coff[tap] + cc * BK,
+                                        w0 + p.tap_dw[tap], p.tap_ph[tap], h0 + p.tap_dh[tap], n0);
+                    } else {
+                        if (NCTA == 2) tma_load_2d_pair(sB0 + stage * Cfg::B_BYTES, &tmB, fb, it * BK, nb * BN + cta_rank * (BN / 2));
+                        else tma_load_2d(sB0 + stage * Cfg::B_BYTES, &tmB, fb, it * BK, nb * BN);
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -229,11 +262,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+        constexpr uint32_t idesc = umma_idesc_bf16(128 * NCTA, BN);
         int stage = 0, as = 0;
         uint32_t phase = 0, aphase = 0;
         int tr_n = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = work0; leader && tile < p.total_tiles; tile += wstride) {
             mbar_wait(tempty(as), aphase ^ 1);
             tc_fence_after();
             if (lane == 0) SKB_TR(1, 1000);
@@ -246,10 +279,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint64_t ad = umma_desc(sA0 + stage * Cfg::A_BYTES, 16, SBO, SW);
                     const uint64_t bd = umma_desc(sB0 + stage * Cfg::B_BYTES, 16, SBO, SW);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16_ss(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(empty(stage));
-                    if (it == p.k_iters - 1) umma_commit(tfull(as));
+                    for (int k = 0; k < BK / 16; ++k) {
+                        if (NCTA == 2) umma_bf16_ss_pair(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
+                        else umma_bf16_ss(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    }
+                    if (NCTA == 2) {  // frees the stage / publishes the accumulator in BOTH CTAs
+                        umma_commit_pair(empty(stage));
+                        if (it == p.k_iters - 1) umma_commit_pair(tfull(as));
+                    } else {
+                        umma_commit(empty(stage));
+                        if (it == p.k_iters - 1) umma_commit(tfull(as));
+                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) {
@@ -280,11 +320,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t sw = row_bytes == 128 ? (uint32_t)(m & 7) : 0u;  // SWIZZLE_128B: 16 B chunk ^= row % 8
         const uint32_t row_off = (uint32_t)m * row_bytes;
         const uint32_t acc = tmem_base + lane_addr + (uint32_t)(g * BN);
-        const int step = 2 * (int)gridDim.x;
+        const int step = 2 * wstride;
         uint32_t qseq = 0;  // running sub-tile number of this group: staging slot = qseq % NB
         uint32_t aphase = 0;
         int tr_n = 0;
-        int tile = (int)blockIdx.x + g * (int)gridDim.x;
+        int tile = work0 + g * wstride;
+        // TMEM stage g is handed back on the LEADER's barrier (the leader issues the pair's MMAs)
+        const uint32_t tempty_g = NCTA == 2 ? mapa_shared(tempty(g), 0) : tempty(g);
+        auto release_tmem = [&]() {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (NCTA == 2) mbar_arrive_cluster(tempty_g);
+                else mbar_arrive(tempty_g);
+            }
+        };
 
         if (!p.up2) {
             auto n_sub = [&](int nb) {
@@ -297,7 +347,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (p.n_blocks == 1) load_bias(0);
             if (T0 && p.has_res && tile < p.total_tiles) {  // residual of the very first sub-tile
                 int nb, w0, h0, n0;
-                decode_tile(p, tile, nb, w0, h0, n0);
+                decode_tile<NCTA>(p, tile, cta_rank, nb, w0, h0, n0);
                 if (n_sub(nb) > 0) {
                     mbar_expect_tx(res_full(g * NB), (uint32_t)p.epi_box_bytes);
                     tma_load_4d(ebuf_g, &tmR, res_full(g * NB), nb * BN, w0, h0, n0);
@@ -306,7 +356,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             named_bar_sync(barid, GT);
             for (; tile < p.total_tiles; tile += step) {
                 int nb, w0, h0, n0;
-                decode_tile(p, tile, nb, w0, h0, n0);
+                decode_tile<NCTA>(p, tile, cta_rank, nb, w0, h0, n0);
                 const int ncol0 = nb * BN;
                 const int nvalid = n_sub(nb);
                 if (T0 && g == 0) SKB_TR(2, 100);
@@ -330,11 +380,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             uint32_t v[32];
                             tmem_ld32(acc + (uint32_t)(c0 + hh * 32), v);
                             tmem_ld_wait();
-                            if (last && hh == pieces - 1) {  // accumulator fully read: hand the TMEM stage back
-                                tc_fence_before();
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive(tempty(g));
-                            }
+                            if (last && hh == pieces - 1) release_tmem();  // accumulator fully read: hand the TMEM stage back
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
                                 epi_chunk_bf16(v + j * 8, sbias_g + 4u * (uint32_t)(c0 + hh * 32 + j * 8), p.act, p.has_res != 0,
@@ -344,11 +390,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         uint32_t v[32];
                         tmem_ld32(acc + (uint32_t)c0, v);
                         tmem_ld_wait();
-                        if (last) {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(tempty(g));
-                        }
+                        if (last) release_tmem();
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             epi_chunk_f32(v + j * 4, sbias_g + 4u * (uint32_t)(c0 + j * 4), p.act, rowp + ((((uint32_t)j) ^ sw) << 4));
@@ -365,7 +407,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             int nb2 = nb, w2 = w0, h2 = h0, n2 = n0, c2 = c0 + sub_cols;
                             bool have = !last;
                             if (last && tile + step < p.total_tiles) {
-                                decode_tile(p, tile + step, nb2, w2, h2, n2);
+                                decode_tile<NCTA>(p, tile + step, cta_rank, nb2, w2, h2, n2);
                                 c2 = 0;
                                 have = n_sub(nb2) > 0;
                             }
@@ -377,11 +419,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     __syncwarp();
                 }
-                if (nvalid == 0) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty(g));
-                }
+                if (nvalid == 0) release_tmem();
                 aphase ^= 1;
             }
             if (T0) tma_store_wait_all();
@@ -395,7 +433,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bool row_in_box = m < p.tn * hw;
             for (; tile < p.total_tiles; tile += step) {
                 int nb, w0, h0, n0;
-                decode_tile(p, tile, nb, w0, h0, n0);
+                decode_tile<NCTA>(p, tile, cta_rank, nb, w0, h0, n0);
                 const int ncol0 = nb * BN;
                 const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
                 const bool valid = row_in_box && n < p.B && h < p.Ho && w < p.Wo;
@@ -407,11 +445,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     uint32_t v[32];
                     tmem_ld32(acc + (uint32_t)c0, v);
                     tmem_ld_wait();
-                    if (c0 + 32 >= BN) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty(g));
-                    }
+                    if (c0 + 32 >= BN) release_tmem();
                     const int ncol = ncol0 + c0;
                     if (valid) {
 #pragma unroll
@@ -461,25 +495,43 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (NCTA == 2) {
+        cluster_sync_all();  // the peer may still be reading operands / signalling barriers in this CTA
+        if (warp == 1) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    } else {
+        __syncthreads();
+        if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BN, int BK>
+template <int BN, int BK, int NCTA>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR, ConvParams p,
                        cudaStream_t stream) {
-    using Cfg = ConvCfg<BN, BK>;
+    using Cfg = ConvCfg<BN, BK, NCTA>;
     static bool attr_set = false;
     if (!attr_set) {
-        SKB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        SKB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BK, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    conv_gemm_kernel<BN, BK><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, p);
-    SKB_LAUNCH_CHECK();
+    const int units = num_sms() / NCTA;  // CTAs (or CTA pairs) resident at once
+    const int grid = (p.total_tiles < units ? p.total_tiles : units) * NCTA;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(352);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NCTA;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SKB_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, BK, NCTA>, tmA, tmB, tmY, tmR, p));
     return SKB_OK;
 }
 
@@ -553,24 +605,42 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
     p.tiles_h = cdiv(Ho, p.th);
     p.tiles_n = cdiv(x->n, p.tn);
     const int m_tiles = p.total_tiles;
-    // output-channel block: minimise waves * per-tile cost (small BN is smem-bandwidth bound)
-    int BN = 32;
+    // Output-channel block BN and CTA pairing: minimise waves * per-tile cost.  Per k-iteration the TMA writes
+    // its operand tiles into shared memory and the MMA reads them back, in 2*BN tensor cycles per SM:
+    //   one CTA : (128+BN) box rows of 128 B per k-iteration    CTA pair: (128+BN/2) rows per CTA
+    // and the TMA engine delivers ~one 128-byte row per 2.4 cycles per SM, so a k-iteration cannot be shorter
+    // than 2.4*(rows) cycles while its MMAs need 2*BN: wide BN amortises the activation rows.
+    int BN = 32, NCTA = 1;
     {
+        // CTA pairs are OFF by default: measured on B200 they do not beat the single-CTA kernel (3x3 128->128
+        // @160: 694 vs 742 TFLOP/s) because the kernel is bound by bytes entering the SM through TMA
+        // (~2.4 cycles per 128-byte box row, ~53 B/clk/SM), not by the shared-memory port.  SKB_CONV_PAIR=1
+        // switches them on for experiments (tuning knob, not part of the ABI).
+        static int pair_mode = -1;
+        if (pair_mode < 0) {
+            const char* e = getenv("SKB_CONV_PAIR");
+            pair_mode = e ? atoi(e) : 0;
+        }
+        const bool pair_ok = pair_mode != 0 && !upsample2x && taps * Cin >= 256 && m_tiles >= 2;
         double best = 1e30;
         const int cands[4] = {256, 128, 64, 32};
-        const double pen[4] = {1.0, 1.0, 1.35, 2.0};
-        for (int i = 0; i < 4; ++i) {
-            if (cout_pad % cands[i]) continue;
-            long tiles = (long)m_tiles * (cout_pad / cands[i]);
-            double cost = (double)cdiv((int)tiles, num_sms()) * cands[i] * pen[i];
-            if (cost < best) {
-                best = cost;
-                BN = cands[i];
+        const double pen1[4] = {1.5, 2.0, 3.0, 5.0};
+        const double pen2[4] = {1.0, 1.5, 2.5, 1e9};
+        for (int nc = 1; nc <= (pair_ok ? 2 : 1); ++nc)
+            for (int i = 0; i < 4; ++i) {
+                if (cout_pad % cands[i]) continue;
+                if (nc == 2 && cands[i] < 64) continue;
+                const long items = (long)cdiv(m_tiles, nc) * (cout_pad / cands[i]);
+                const double cost = (double)cdiv((int)items, num_sms() / nc) * cands[i] * (nc == 2 ? pen2[i] : pen1[i]);
+                if (cost < best) {
+                    best = cost;
+                    BN = cands[i];
+                    NCTA = nc;
+                }
             }
-        }
     }
     p.n_blocks = cout_pad / BN;
-    p.total_tiles = m_tiles * p.n_blocks;
+    p.total_tiles = cdiv(m_tiles, NCTA) * p.n_blocks;  // work items: one per CTA, or per CTA pair
     p.fd_nb = make_fastdiv(p.n_blocks); p.fd_tw = make_fastdiv(p.tiles_w); p.fd_th = make_fastdiv(p.tiles_h);
     p.B = x->n; p.Ho = Ho; p.Wo = Wo;
     p.cchunks = Cin / BK;
@@ -615,7 +685,7 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
         if (rc != SKB_OK) return rc;
         uint64_t bd[2] = {(uint64_t)taps * Cin, (uint64_t)cout_pad};
         uint64_t bs[1] = {(uint64_t)taps * Cin * 2};
-        uint32_t bb[2] = {(uint32_t)BK, (uint32_t)BN};
+        uint32_t bb[2] = {(uint32_t)BK, (uint32_t)(BN / NCTA)};
         rc = encode_tensor_map(&tmB, w_packed, 2, 2, bd, bs, bb, BK * 2);
         if (rc != SKB_OK) return rc;
         // epilogue maps: 4-D {c, w, h, n} boxes of sub_cols channels x (tw, th, tn) pixels, 128-byte rows
@@ -642,13 +712,15 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
         }
     }
     cudaStream_t st = (cudaStream_t)stream;
-#define SKB_CONV_CASE(bn, bk) \
-    if (BN == bn && BK == bk) return launch_conv<bn, bk>(tmA, tmB, tmY, tmR, p, st);
-    SKB_CONV_CASE(256, 64) SKB_CONV_CASE(128, 64) SKB_CONV_CASE(64, 64) SKB_CONV_CASE(32, 64)
-    SKB_CONV_CASE(256, 32) SKB_CONV_CASE(128, 32) SKB_CONV_CASE(64, 32) SKB_CONV_CASE(32, 32)
-    SKB_CONV_CASE(256, 16) SKB_CONV_CASE(128, 16) SKB_CONV_CASE(64, 16) SKB_CONV_CASE(32, 16)
+#define SKB_CONV_CASE(bn, bk, nc) \
+    if (BN == bn && BK == bk && NCTA == nc) return launch_conv<bn, bk, nc>(tmA, tmB, tmY, tmR, p, st);
+    SKB_CONV_CASE(256, 64, 1) SKB_CONV_CASE(128, 64, 1) SKB_CONV_CASE(64, 64, 1) SKB_CONV_CASE(32, 64, 1)
+    SKB_CONV_CASE(256, 32, 1) SKB_CONV_CASE(128, 32, 1) SKB_CONV_CASE(64, 32, 1) SKB_CONV_CASE(32, 32, 1)
+    SKB_CONV_CASE(256, 16, 1) SKB_CONV_CASE(128, 16, 1) SKB_CONV_CASE(64, 16, 1) SKB_CONV_CASE(32, 16, 1)
+    SKB_CONV_CASE(256, 64, 2) SKB_CONV_CASE(128, 64, 2) SKB_CONV_CASE(64, 64, 2)
+    SKB_CONV_CASE(256, 32, 2) SKB_CONV_CASE(128, 32, 2) SKB_CONV_CASE(64, 32, 2)
 #undef SKB_CONV_CASE
-    set_error("conv2d: no kernel for BN=%d BK=%d", BN, BK);
+    set_error("conv2d: no kernel for BN=%d BK=%d NCTA=%d", BN, BK, NCTA);
     return SKB_ERR_UNSUPPORTED;
 }
 
@@ -724,7 +796,7 @@ extern "C" int skb_focus_conv_bf16(const void* img, int32_t img_dtype, int32_t n
         rc = encode_tensor_map(&tmY, y->ptr, 2, 4, yd, ys, yb, row_bytes == 128 ? 128 : 0);
         if (rc != SKB_OK) return rc;
     }
-    if (BN == 128) return launch_conv<128, 64>(tmA, tmB, tmY, tmB, p, st);
-    if (BN == 64) return launch_conv<64, 64>(tmA, tmB, tmY, tmB, p, st);
-    return launch_conv<32, 64>(tmA, tmB, tmY, tmB, p, st);
+    if (BN == 128) return launch_conv<128, 64, 1>(tmA, tmB, tmY, tmB, p, st);
+    if (BN == 64) return launch_conv<64, 64, 1>(tmA, tmB, tmY, tmB, p, st);
+    return launch_conv<32, 64, 1>(tmA, tmB, tmY, tmB, p, st);
 }
