@@ -504,6 +504,297 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
+// =============================================================================================
+// 3x3 stride-1 conv with a shared-memory HALO tile (the bottleneck convs of every CSP block).
+//
+// The generic kernel above fetches the activation tile once per filter tap (9x) and its weight tile once
+// per 128 pixels; on B200 it is bound by bytes entering the SM through TMA (~53 B/clk/SM measured), not
+// by the tensor pipe (37-43 % busy).  Here one CTA owns a 16 x 16 pixel tile (two 128-row accumulators,
+// left and right 8-pixel halves):
+//   * per 64-channel chunk the TMA engine loads ONE 18 x 24 pixel halo box (54 KB, rows padded to 24 pixels
+//     so a pixel row is 3 swizzle atoms) and all 9 taps read it in place: the A operand of tap (dy, dx) and
+//     half a is the same smem tile addressed at +dy*3072 + (8a + dx)*128 bytes with SBO = 3072 -- a UMMA
+//     descriptor whose start is not 1024-aligned (the hardware swizzle follows absolute address bits, so the
+//     TMA-written pattern and the MMA read agree; the descriptor's base-offset field stays 0);
+//   * every weight tile (BN x 64, one per tap and chunk) is used by both accumulators.
+// Bytes into the SM per 256 pixels: 54 KB*chunks + 9*chunks*BN*128 B, vs 2*9*chunks*(16 KB + BN*128 B) before
+// (128->128: 396 KB vs 1152 KB), which makes these layers tensor-bound.
+// Warp roles: 0 = halo TMA producer, 10 = weight TMA producer, 1 = MMA issuer, 2..5 / 6..9 = epilogue of the
+// left / right accumulator.  TMEM: 2 tiles in flight x 2 halves x BN columns.
+// =============================================================================================
+struct HaloParams {
+    int tiles_w, tiles_h;
+    int n_blocks, total_items;
+    FastDiv fd_nb, fd_tw, fd_th;
+    int cchunks, cin;
+    int cout;
+    const float* bias;
+    int act, has_res;
+    long long* trace;
+};
+
+template <int BN>
+struct HaloCfg {
+    static constexpr int HALO_W = 24, HALO_H = 18;
+    static constexpr int HALO_BYTES = HALO_H * HALO_W * 128;  // 55296
+    static constexpr int HS = 2;                              // halo stages
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int EPI_NB = BN == 64 ? 2 : 1;           // staging slots per epilogue group
+    static constexpr int EPI_BUF = 16384;
+    static constexpr int EPI_BYTES = 2 * EPI_NB * EPI_BUF + 2 * BN * 4;
+    static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - EPI_BYTES - HS * HALO_BYTES;
+    static constexpr int BS = (BUDGET / B_BYTES) < 8 ? (BUDGET / B_BYTES) : 8;  // weight stages
+    static constexpr int TMEM_COLS = 4 * BN;                  // 256 or 512
+    static constexpr int SMEM_BYTES = HS * HALO_BYTES + BS * B_BYTES + EPI_BYTES + 1024 + 512;
+};
+
+__device__ __forceinline__ void halo_decode(const HaloParams& p, int item, int& nb, int& w0, int& h0, int& n) {
+    int t, iw, ih;
+    fast_divmod(p.fd_nb, item, t, nb);
+    fast_divmod(p.fd_tw, t, t, iw);
+    fast_divmod(p.fd_th, t, n, ih);
+    w0 = iw * 16; h0 = ih * 16;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(352, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const HaloParams p) {
+    using Cfg = HaloCfg<BN>;
+    constexpr int HS = Cfg::HS, BS = Cfg::BS, NB = Cfg::EPI_NB;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t sH0 = base;
+    const uint32_t sB0 = base + HS * Cfg::HALO_BYTES;
+    const uint32_t ebuf0 = sB0 + BS * Cfg::B_BYTES;
+    const uint32_t sbias = ebuf0 + 2 * NB * Cfg::EPI_BUF;
+    const uint32_t bar0 = sbias + 2 * BN * 4;
+    auto h_full = [&](int s) { return bar0 + 8u * s; };
+    auto h_empty = [&](int s) { return bar0 + 8u * (HS + s); };
+    auto b_full = [&](int s) { return bar0 + 8u * (2 * HS + s); };
+    auto b_empty = [&](int s) { return bar0 + 8u * (2 * HS + BS + s); };
+    auto tfull = [&](int s) { return bar0 + 8u * (2 * HS + 2 * BS + s); };
+    auto tempty = [&](int s) { return bar0 + 8u * (2 * HS + 2 * BS + 2 + s); };
+    auto res_full = [&](int s) { return bar0 + 8u * (2 * HS + 2 * BS + 4 + s); };
+    const uint32_t slot = bar0 + 8u * (2 * HS + 2 * BS + 4 + 2 * NB);
+    volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmY);
+        if (p.has_res) tma_prefetch_desc(&tmR);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < HS; ++s) { mbar_init(h_full(s), 1); mbar_init(h_empty(s), 1); }
+            for (int s = 0; s < BS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+            for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 8); }
+            for (int s = 0; s < 2 * NB; ++s) mbar_init(res_full(s), 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(slot, Cfg::TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *slot_ptr;
+
+    if (warp == 0) {
+        // ===================== halo producer =====================
+        if (lane == 0) {
+            int hs = 0;
+            uint32_t hph = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                int nb, w0, h0, n;
+                halo_decode(p, item, nb, w0, h0, n);
+                for (int c = 0; c < p.cchunks; ++c) {
+                    mbar_wait(h_empty(hs), hph ^ 1);
+                    mbar_expect_tx(h_full(hs), (uint32_t)Cfg::HALO_BYTES);
+                    tma_load_4d(sH0 + hs * Cfg::HALO_BYTES, &tmA, h_full(hs), c * 64, w0 - 1, h0 - 1, n);  // borders: zero fill
+                    if (++hs == HS) { hs = 0; hph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 10) {
+        // ===================== weight producer =====================
+        if (lane == 0) {
+            int bs = 0;
+            uint32_t bph = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                int nb, w0, h0, n;
+                halo_decode(p, item, nb, w0, h0, n);
+                for (int c = 0; c < p.cchunks; ++c)
+                    for (int t = 0; t < 9; ++t) {
+                        mbar_wait(b_empty(bs), bph ^ 1);
+                        mbar_expect_tx(b_full(bs), (uint32_t)Cfg::B_BYTES);
+                        tma_load_2d(sB0 + bs * Cfg::B_BYTES, &tmB, b_full(bs), t * p.cin + c * 64, nb * BN);
+                        if (++bs == BS) { bs = 0; bph ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+        int hs = 0, bs = 0, buf = 0;
+        uint32_t hph = 0, bph = 0, tph = 0;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            mbar_wait(tempty(buf), tph ^ 1);
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + (uint32_t)((buf * 2) * BN), d1 = d0 + (uint32_t)BN;
+            for (int c = 0; c < p.cchunks; ++c) {
+                mbar_wait(h_full(hs), hph);
+                const uint32_t hbase = sH0 + hs * Cfg::HALO_BYTES;
+                for (int t = 0; t < 9; ++t) {
+                    mbar_wait(b_full(bs), bph);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const int dy = t / 3, dx = t - dy * 3;
+                        const uint32_t a0 = hbase + (uint32_t)(dy * 3072 + dx * 128);
+                        // start not 1024-aligned when dx != 0: the 128B-swizzle XOR is taken from the absolute smem
+                        // address bits [7,10) (measured: correct with the descriptor's base-offset field left 0)
+                        const uint64_t ad0 = umma_desc(a0, 16, 3072, UMMA_SW128);
+                        const uint64_t ad1 = umma_desc(a0 + 1024, 16, 3072, UMMA_SW128);  // right half: 8 pixels further
+                        const uint64_t bd = umma_desc(sB0 + bs * Cfg::B_BYTES, 16, 1024, UMMA_SW128);
+                        const uint32_t acc = (c > 0 || t > 0) ? 1u : 0u;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16_ss(d0, ad0 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (acc || k > 0) ? 1u : 0u);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16_ss(d1, ad1 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (acc || k > 0) ? 1u : 0u);
+                        umma_commit(b_empty(bs));
+                        if (t == 8) {
+                            umma_commit(h_empty(hs));
+                            if (c == p.cchunks - 1) umma_commit(tfull(buf));
+                        }
+                    }
+                    __syncwarp();
+                    if (++bs == BS) { bs = 0; bph ^= 1; }
+                }
+                if (++hs == HS) { hs = 0; hph ^= 1; }
+            }
+            buf ^= 1;
+            if (buf == 0) tph ^= 1;
+        }
+    } else {
+        // ===================== epilogue: group g = accumulator half g (pixels w0 + 8g .. w0 + 8g + 7) =====================
+        constexpr int GT = 128;
+        const int g = (warp - 2) >> 2;
+        const int q = warp & 3;
+        const int m = q * 32 + lane;               // accumulator row = (row m / 8, pixel m % 8) of the half tile
+        const int tg = (int)threadIdx.x - 64 - g * GT;
+        const bool T0 = tg == 0;
+        const int barid = 1 + g;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const uint32_t ebuf_g = ebuf0 + (uint32_t)(g * NB) * Cfg::EPI_BUF;
+        const uint32_t sbias_g = sbias + (uint32_t)(g * BN) * 4u;
+        const uint32_t sw = (uint32_t)(m & 7);
+        const uint32_t row_off = (uint32_t)m * 128u;
+        constexpr int NSUB = BN / 64;
+        uint32_t qseq = 0;
+        int buf = 0;
+        uint32_t tph = 0;
+        auto load_bias = [&](int nb) {
+            for (int i = tg; i < BN; i += GT) sts32f(sbias_g + 4u * i, __ldg(p.bias + nb * BN + i));
+        };
+        int item = blockIdx.x;
+        if (p.n_blocks == 1) load_bias(0);
+        if (T0 && p.has_res && item < p.total_items) {
+            int nb, w0, h0, n;
+            halo_decode(p, item, nb, w0, h0, n);
+            mbar_expect_tx(res_full(g * NB), (uint32_t)Cfg::EPI_BUF);
+            tma_load_4d(ebuf_g, &tmR, res_full(g * NB), nb * BN, w0 + 8 * g, h0, n);
+        }
+        named_bar_sync(barid, GT);
+        for (; item < p.total_items; item += gridDim.x) {
+            int nb, w0, h0, n;
+            halo_decode(p, item, nb, w0, h0, n);
+            const int ncol0 = nb * BN;
+            if (p.n_blocks > 1) {
+                load_bias(nb);
+                named_bar_sync(barid, GT);
+            }
+            const uint32_t acc = tmem_base + lane_addr + (uint32_t)((buf * 2 + g) * BN);
+            mbar_wait(tfull(buf), tph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int sub = 0; sub < NSUB; ++sub, ++qseq) {
+                const uint32_t slot_i = qseq % NB;
+                const uint32_t bufa = ebuf_g + slot_i * Cfg::EPI_BUF;
+                const int c0 = sub * 64;
+                const uint32_t rowp = bufa + row_off;
+                const bool last = sub == NSUB - 1;
+                if (p.has_res) mbar_wait(res_full(g * NB + slot_i), (qseq / NB) & 1u);
+#pragma unroll 1
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t v[32];
+                    tmem_ld32(acc + (uint32_t)(c0 + hh * 32), v);
+                    tmem_ld_wait();
+                    if (last && hh == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty(buf));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        epi_chunk_bf16(v + j * 8, sbias_g + 4u * (uint32_t)(c0 + hh * 32 + j * 8), p.act, p.has_res != 0,
+                                       rowp + ((((uint32_t)(hh * 4 + j)) ^ sw) << 4));
+                }
+                if (NB == 2 && T0) tma_store_wait_read<0>();  // store(q-1) has drained the other slot
+                fence_proxy_async_smem();
+                named_bar_sync(barid, GT);
+                if (T0) {
+                    tma_store_4d(&tmY, bufa, ncol0 + c0, w0 + 8 * g, h0, n);
+                    tma_store_commit();
+                    if (NB == 1) tma_store_wait_read<0>();    // single slot: it must drain before it is refilled
+                    if (p.has_res) {  // residual of the group's next sub-tile
+                        int nb2 = nb, w2 = w0, h2 = h0, n2 = n, c2 = c0 + 64;
+                        bool have = !last;
+                        if (last && item + (int)gridDim.x < p.total_items) {
+                            halo_decode(p, item + (int)gridDim.x, nb2, w2, h2, n2);
+                            c2 = 0;
+                            have = true;
+                        }
+                        if (have) {
+                            const uint32_t s2 = (qseq + 1) % NB;
+                            mbar_expect_tx(res_full(g * NB + s2), (uint32_t)Cfg::EPI_BUF);
+                            tma_load_4d(ebuf_g + s2 * Cfg::EPI_BUF, &tmR, res_full(g * NB + s2), nb2 * BN + c2, w2 + 8 * g, h2, n2);
+                        }
+                    }
+                }
+                if (NB == 1) named_bar_sync(barid, GT);       // nobody refills the slot before it has drained
+                else __syncwarp();
+            }
+            buf ^= 1;
+            if (buf == 0) tph ^= 1;
+        }
+        if (T0) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN>
+static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR, const HaloParams& p,
+                       cudaStream_t stream) {
+    using Cfg = HaloCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SKB_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int grid = p.total_items < num_sms() ? p.total_items : num_sms();
+    conv3x3_halo_kernel<BN><<<grid, 352, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, p);
+    SKB_LAUNCH_CHECK();
+    return SKB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -597,6 +888,57 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
     }
     const int BK = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);  // K chunk = swizzle span (128 / 64 / 32 B rows)
     const int taps = ksize * ksize;
+
+    // ---- 3x3 stride-1: halo-tile kernel when 16 x 16 pixel tiles cover the map with little waste ----
+    {
+        static int halo_mode = -1;  // tuning knob (not part of the ABI): SKB_CONV_HALO=0 forces the generic kernel
+        if (halo_mode < 0) {
+            const char* e = getenv("SKB_CONV_HALO");
+            halo_mode = e ? atoi(e) : 1;
+        }
+        const int th16 = cdiv(Ho, 16), tw16 = cdiv(Wo, 16);
+        const double cover = (double)th16 * 16 * tw16 * 16 / ((double)Ho * Wo);
+        if (halo_mode && ksize == 3 && stride == 1 && !upsample2x && Cin % 64 == 0 && y->dtype == SKB_BF16 && cout_pad % 64 == 0 &&
+            cover <= 1.2) {
+            const int BN = cout_pad % 128 == 0 ? 128 : 64;
+            HaloParams hp;
+            memset(&hp, 0, sizeof(hp));
+            hp.tiles_w = tw16; hp.tiles_h = th16;
+            hp.n_blocks = cout_pad / BN;
+            hp.total_items = tw16 * th16 * x->n * hp.n_blocks;
+            hp.fd_nb = make_fastdiv(hp.n_blocks); hp.fd_tw = make_fastdiv(tw16); hp.fd_th = make_fastdiv(th16);
+            hp.cchunks = Cin / 64; hp.cin = Cin; hp.cout = y->c;
+            hp.bias = bias; hp.act = act; hp.has_res = residual ? 1 : 0; hp.trace = g_conv_trace;
+            CUtensorMap tmA, tmB, tmY, tmR;
+            const uint64_t pitchB = (uint64_t)x->pitch * 2;
+            uint64_t ad[4] = {(uint64_t)Cin, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
+            uint64_t as[3] = {pitchB, pitchB * x->w, pitchB * x->w * x->h};
+            uint32_t ab[4] = {64u, 24u, 18u, 1u};
+            rc = encode_tensor_map(&tmA, x->ptr, 2, 4, ad, as, ab, 128);
+            if (rc != SKB_OK) return rc;
+            uint64_t bd[2] = {(uint64_t)taps * Cin, (uint64_t)cout_pad};
+            uint64_t bs[1] = {(uint64_t)taps * Cin * 2};
+            uint32_t bb[2] = {64u, (uint32_t)BN};
+            rc = encode_tensor_map(&tmB, w_packed, 2, 2, bd, bs, bb, 128);
+            if (rc != SKB_OK) return rc;
+            uint64_t yd[4] = {(uint64_t)y->c, (uint64_t)y->w, (uint64_t)y->h, (uint64_t)y->n};
+            uint64_t ys[3] = {(uint64_t)y->pitch * 2, (uint64_t)y->pitch * 2 * y->w, (uint64_t)y->pitch * 2 * y->w * y->h};
+            uint32_t yb[4] = {64u, 8u, 16u, 1u};
+            rc = encode_tensor_map(&tmY, y->ptr, 2, 4, yd, ys, yb, 128);
+            if (rc != SKB_OK) return rc;
+            if (residual) {
+                uint64_t rd[4] = {(uint64_t)residual->c, (uint64_t)residual->w, (uint64_t)residual->h, (uint64_t)residual->n};
+                uint64_t rs[3] = {(uint64_t)residual->pitch * 2, (uint64_t)residual->pitch * 2 * residual->w,
+                                  (uint64_t)residual->pitch * 2 * residual->w * residual->h};
+                rc = encode_tensor_map(&tmR, residual->ptr, 2, 4, rd, rs, yb, 128);
+                if (rc != SKB_OK) return rc;
+            } else {
+                tmR = tmB;
+            }
+            return BN == 128 ? launch_halo<128>(tmA, tmB, tmY, tmR, hp, (cudaStream_t)stream)
+                             : launch_halo<64>(tmA, tmB, tmY, tmR, hp, (cudaStream_t)stream);
+        }
+    }
 
     ConvParams p;
     memset(&p, 0, sizeof(p));

@@ -93,6 +93,17 @@ def test_conv_bf16_store(case):
     assert err < TOL_BF16, err
 
 
+def test_conv_halo_kernel_residual_and_slices():
+    # 3x3 stride-1 layers whose map is covered by 16x16 tiles run the halo-tile kernel (conv_gemm.cu)
+    assert _run(2, 32, 32, 128, 128, 3, 1, residual=True, out_f32=False) < TOL_BF16      # BN = 128: one staging slot
+    assert _run(1, 32, 48, 64, 64, 3, 1, residual=True, out_f32=False) < TOL_BF16        # BN = 64: two staging slots
+    assert _run(1, 16, 32, 64, 64, 3, 1, slice_in=64, slice_out=64, out_f32=False) < TOL_BF16
+    assert _run(3, 16, 16, 256, 256, 3, 1, residual=True, out_f32=False) < TOL_BF16      # 4 chunks x 2 channel blocks
+    assert _run(1, 30, 46, 64, 128, 3, 1, out_f32=False) < TOL_BF16                      # ragged tiles in both directions
+    assert _run(2, 32, 16, 192, 64, 3, 1, out_f32=False, act=2) < TOL_BF16               # three chunks, ReLU
+    assert _run(1, 48, 32, 128, 256, 3, 1, out_f32=False, act=0) < TOL_BF16              # two channel blocks, linear
+
+
 def test_conv_residual_after_activation():
     # the residual path stores bf16 (bottlenecks, transformer residuals); fp32 + residual is not on the path
     assert _run(2, 16, 16, 128, 128, 3, 1, residual=True, out_f32=False) < TOL_BF16
