@@ -11,13 +11,13 @@
 //   O += P V          tcgen05.mma with A = P from TMEM, B = V consumed MN-major straight from its TMA tile
 // Shared memory therefore carries only the K/V stream (the smem port is shared by TMA writes and MMA
 // operand reads and was the co-bottleneck with P and Q staged there).  The softmax is MUFU-bound
-// (64 flop per exponential at head_dim 64), so ATT_POLY of every 64 exponentials are evaluated on the
+// (64 flop per exponential at head_dim 64); ATT_POLY of every 64 exponentials can be evaluated on the
 // FMA pipes instead (Cody-Waite split + degree-3 polynomial, rel. error 7.5e-5 << bf16), in packed
-// fp32x2 arithmetic.  MMAs of one CTA execute in issue order, which is what lets QK(j+2) reuse the
+// fp32x2 arithmetic.  The softmax denominator is produced by the PV MMA itself (16 all-ones B columns).  MMAs of one CTA execute in issue order, which is what lets QK(j+2) reuse the
 // S/P buffer of tile j right after PV(j) has been issued.
 // The in_proj output [B, N, 3C] is read in place: one 3-D tensor map {channel, token, image} serves
 // Q, K and V (different channel coordinates), ragged N is TMA zero fill + a -inf mask on the last tile.
-// 2 CTAs are resident per SM (81 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the
+// 2 CTAs are resident per SM (89 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the
 // other's MMAs.  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = softmax/epilogue.
 #include <math.h>
 #include <stdlib.h>
@@ -29,9 +29,11 @@ namespace skb {
 constexpr int ATT_BQ = 128, ATT_BKV = 64, ATT_D = 64, ATT_KVS = 4;
 constexpr int ATT_Q_BYTES = ATT_BQ * ATT_D * 2;     // 16 KB
 constexpr int ATT_KV_BYTES = ATT_BKV * ATT_D * 2;   // 8 KB
-constexpr int ATT_SMEM = ATT_Q_BYTES + 2 * ATT_KVS * ATT_KV_BYTES + 1024 + 256;
-constexpr uint32_t ATT_TMEM_COLS = 256;             // S0/P0 [0,64) S1/P1 [64,128) O [128,192) Q [192,224)
-constexpr int ATT_POLY_DEFAULT = 8;                 // exponentials per 64 evaluated on the FMA pipes (0, 8, 16, 24, 32)
+constexpr int ATT_ONES_BYTES = ATT_BKV * 128;       // 8 KB of bf16 1.0: extra B columns that make the PV MMA emit the row sums
+constexpr int ATT_SMEM = ATT_Q_BYTES + 2 * ATT_KVS * ATT_KV_BYTES + ATT_ONES_BYTES + 1024 + 256;
+constexpr int ATT_ON = ATT_D + 16;                  // PV accumulator width: 64 output dims + 16 copies of sum_k P
+constexpr uint32_t ATT_TMEM_COLS = 256;             // S0/P0 [0,64) S1/P1 [64,128) O [128,208) Q [208,240)
+constexpr int ATT_POLY_DEFAULT = 0;                 // exponentials per 64 evaluated on the FMA pipes (0, 8, 16, 24, 32)
 
 struct AttnParams {
     int N, heads, C, T;
@@ -82,7 +84,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t sQ = base;
     const uint32_t sK0 = sQ + ATT_Q_BYTES;
     const uint32_t sV0 = sK0 + ATT_KVS * ATT_KV_BYTES;
-    const uint32_t bar0 = sV0 + ATT_KVS * ATT_KV_BYTES;
+    const uint32_t sOnes = sV0 + ATT_KVS * ATT_KV_BYTES;
+    const uint32_t bar0 = sOnes + ATT_ONES_BYTES;
     const uint32_t q_full = bar0;
     const uint32_t q_ready = bar0 + 8u;
     auto kv_full = [&](int s) { return bar0 + 8u * (2 + s); };
@@ -118,7 +121,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tc_fence_after();
     const uint32_t tmem = *slot_ptr;
     const uint32_t tmem_O = tmem + 128;
-    const uint32_t tmem_Q = tmem + 192;
+    const uint32_t tmem_L = tmem_O + ATT_D;  // row sums (first of 16 identical columns)
+    const uint32_t tmem_Q = tmem + 208;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -137,7 +141,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BQ, ATT_BKV, 0, 0);  // A = Q (TMEM), B = K (K-major)
-        constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BQ, ATT_D, 0, 1);    // A = P (TMEM), B = V (MN-major)
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BQ, ATT_ON, 0, 1);   // A = P (TMEM), B = [V | ones] (MN-major)
         auto issue_qk = [&](int j) {
             const int s = j % ATT_KVS, sb = j & 1;
             mbar_wait(kv_full(s), (uint32_t)(j / ATT_KVS) & 1u);
@@ -160,8 +164,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             mbar_wait(p_full(sb), (uint32_t)(j >> 1) & 1u);
             tc_fence_after();
             if (lane == 0) {
-                // V tile [64 keys][64 d]: MN-major, 128-byte rows, 8-row groups 1024 B apart, 16 keys per MMA = 2048 B
-                const uint64_t bd = umma_desc(sV0 + s * ATT_KV_BYTES, 1024, 1024, UMMA_SW128);
+                // V tile [64 keys][64 d]: MN-major, 128-byte rows, 8-row groups 1024 B apart, 16 keys per MMA = 2048 B.
+                // N = 80: the second 64-wide N atom (leading-dimension offset) is the all-ones tile, so columns
+                // 64..79 of the accumulator receive sum_k P[q][k] -- the softmax denominator comes out of the
+                // tensor core (and is the sum of exactly the bf16 values that multiply V).
+                const uint32_t vaddr = sV0 + s * ATT_KV_BYTES;
+                const uint64_t bd = umma_desc(vaddr, sOnes - vaddr, 1024, UMMA_SW128);
 #pragma unroll
                 for (int k = 0; k < ATT_BKV / 16; ++k)
                     umma_bf16_ts(tmem_O, tmem + sb * ATT_BKV + k * 8, bd + (uint64_t)(k * 128), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
@@ -185,12 +193,18 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 qr[4 * c + 0] = u.x; qr[4 * c + 1] = u.y; qr[4 * c + 2] = u.z; qr[4 * c + 3] = u.w;
             }
             tmem_st32(tmem_Q + lane_addr, qr);
+            {   // all-ones B tile (bf16 1.0 = 0x3F80): 128 threads x 64 bytes
+                const uint4 one4 = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) sts128(sOnes + (uint32_t)row * 64u + (uint32_t)(c << 4), one4);
+                fence_proxy_async_smem();
+            }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(q_ready);
         }
-        float m_ref = -INFINITY, l = 0.f;
+        float m_ref = -INFINITY;
         const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
         for (int j = 0; j < T; ++j) {
             const int sb = j & 1;
@@ -211,6 +225,27 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 for (int i = 0; i < 64; ++i)
                     if (kbase + i >= p.N) sv[i] = 0xff800000u;  // -inf
             }
+            // P = exp2(S*c - m_ref), bf16 pairs; every (64 / ATT_POLY)-th pair runs on the FMA pipes
+            uint32_t pk[32];
+            auto compute_p = [&](float mref) {
+                const float2 nm2 = make_float2(-mref, -mref);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {  // pair i = keys 2i, 2i+1
+                    const float2 x = ffma2(make_float2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sc2, nm2);
+                    float2 e;
+                    if (ATT_POLY > 0 && ((i + 1) * ATT_POLY / 64) != (i * ATT_POLY / 64)) {
+                        e = exp2_poly2(x);
+                    } else {
+                        e.x = ex2_approx(x.x);
+                        e.y = ex2_approx(x.y);
+                    }
+                    pk[i] = pack_bf16x2(e.x, e.y);
+                }
+            };
+            // Speculate that the reference max does not move (true for all but the first few tiles): the
+            // exponentials start right after the TMEM load and the row max is computed alongside them instead
+            // of in front of them (it was a ~120-cycle dependent chain ahead of the MUFU-bound phase).
+            compute_p(m_ref);
             float mx;
             {   // 8 independent chains instead of one 64-deep dependent FMNMX chain
                 float m8[8];
@@ -223,46 +258,33 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             mx *= p.scale_log2;  // log2 domain (scale > 0)
             // lazy reference max: rescale only if some row's max grew by more than 8 (p stays <= 2^8)
             const bool need = mx > m_ref + 8.0f;
-            const bool any = __any_sync(0xffffffffu, need);
-            const float m_new = need ? mx : m_ref;
-            if (any && j > 0) {
-                mbar_wait(o_done, (uint32_t)(j - 1) & 1u);  // PV(j-1) complete: O quiescent (PV(j) waits for our P)
-                tc_fence_after();
-                const float alpha = need ? exp2f(m_ref - m_new) : 1.0f;
-                l *= alpha;
+            if (__any_sync(0xffffffffu, need)) {  // rare: redo the tile against the new reference
+                const float m_new = need ? mx : m_ref;
+                if (j > 0) {
+                    mbar_wait(o_done, (uint32_t)(j - 1) & 1u);  // PV(j-1) complete: O quiescent (PV(j) waits for our P)
+                    tc_fence_after();
+                    const float alpha = need ? exp2f(m_ref - m_new) : 1.0f;
+                    {
+                        const uint32_t lsum = tmem_ld1(tmem_L + lane_addr);
+                        tmem_ld_wait();
+                        tmem_st1(tmem_L + lane_addr, __float_as_uint(__uint_as_float(lsum) * alpha));
+                    }
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t o[32];
-                    tmem_ld32(tmem_O + lane_addr + h * 32, o);
-                    tmem_ld_wait();
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t o[32];
+                        tmem_ld32(tmem_O + lane_addr + h * 32, o);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                    tmem_st32(tmem_O + lane_addr + h * 32, o);
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(tmem_O + lane_addr + h * 32, o);
+                    }
+                    tmem_st_wait();
                 }
-                tmem_st_wait();
-            }
-            m_ref = m_new;
-            const float2 nm2 = make_float2(-m_ref, -m_ref);
-            float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-            uint32_t pk[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {  // pair i = keys 2i, 2i+1; every (64 / ATT_POLY)-th pair runs on the FMA pipes
-                const float2 x = ffma2(make_float2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sc2, nm2);
-                float2 e;
-                // pairs on the FMA pipes: POLY/2 of the 32 pairs, spread evenly (i*POLY/64 increments)
-                if (ATT_POLY > 0 && ((i + 1) * ATT_POLY / 64) != (i * ATT_POLY / 64)) {
-                    e = exp2_poly2(x);
-                } else {
-                    e.x = ex2_approx(x.x);
-                    e.y = ex2_approx(x.y);
-                }
-                acc[i & 3] = fadd2(acc[i & 3], e);
-                pk[i] = pack_bf16x2(e.x, e.y);
+                m_ref = m_new;
+                compute_p(m_ref);
             }
             // P (bf16, K-major: lane = query row, column c holds keys 2c, 2c+1) over the first half of S
             tmem_st32(tmem + lane_addr + sb * ATT_BKV, pk);
-            const float2 a01 = fadd2(fadd2(acc[0], acc[1]), fadd2(acc[2], acc[3]));
-            l += a01.x + a01.y;
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -271,7 +293,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         // ---- epilogue: O / l -> bf16 ----
         mbar_wait(o_done, (uint32_t)(T - 1) & 1u);
         tc_fence_after();
-        const float inv = 1.0f / l;
+        const uint32_t lsum = tmem_ld1(tmem_L + lane_addr);
+        tmem_ld_wait();
+        const float inv = 1.0f / __uint_as_float(lsum);
         const int token = qt * ATT_BQ + row;
         __nv_bfloat16* dst = p.out + ((long)b * p.N + token) * p.out_pitch + head * ATT_D;
 #pragma unroll
