@@ -284,6 +284,32 @@ def run_b200(args):
     ms_e2e = timed(step_e2e, args.steps)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
 
+    # p50 batch-1 latency (second half of BASELINE.json's metric): one resident image through model(x) + NMS
+    latency = None
+    if world == 1:
+        x1 = x_dev[:1].contiguous()
+        o1 = torch.zeros((1, MAX_DET, 7), dtype=torch.float32, device=dev)
+        c1 = torch.zeros(1, dtype=torch.int32, device=dev)
+
+        def step_b1():
+            d1, _ = model(x1)
+            batched_nms_padded(d1, CONF, IOU, max_detections=MAX_DET, out=o1, out_count=c1)
+
+        for _ in range(3):
+            step_b1()
+        torch.cuda.synchronize()
+        lat = []
+        for _ in range(30):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_b1()
+            b.record()
+            torch.cuda.synchronize()
+            lat.append(a.elapsed_time(b))
+        lat.sort()
+        latency = {"p50_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)], "min_ms": lat[0], "samples": len(lat),
+                   "scope": f"{args.variant} {S}x{S} batch 1: model(x) + NMS, image resident, CUDA events"}
+
     launches_per_step = plan.launches + NMS_LAUNCHES
     from skyeye.engine import View
     act_gb = sum(v.t.numel() * v.t.element_size() for v in plan.keep if isinstance(v, View)) / 1e9
@@ -309,6 +335,7 @@ def run_b200(args):
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "latency_b1": latency,
             "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in table.items()},
         }
         print(json.dumps(line))

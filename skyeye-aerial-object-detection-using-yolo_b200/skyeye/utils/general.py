@@ -49,3 +49,53 @@ def load_images(source, img_size=640):
         batch[b, : im.shape[0], : im.shape[1]] = im
     t = torch.from_numpy(np.ascontiguousarray(batch[..., ::-1].transpose(0, 3, 1, 2))).float() / 255.0
     return t, names, origs
+
+
+def xywh2xyxy(x):
+    """[cx, cy, w, h] -> [x1, y1, x2, y2] (imported but never defined by the reference, validate.py:21-24)."""
+    y = x.clone() if isinstance(x, torch.Tensor) else np.copy(x)
+    y[..., 0] = x[..., 0] - x[..., 2] / 2
+    y[..., 1] = x[..., 1] - x[..., 3] / 2
+    y[..., 2] = x[..., 0] + x[..., 2] / 2
+    y[..., 3] = x[..., 1] + x[..., 3] / 2
+    return y
+
+
+def xyxy2xywh(x):
+    """[x1, y1, x2, y2] -> [cx, cy, w, h]."""
+    y = x.clone() if isinstance(x, torch.Tensor) else np.copy(x)
+    y[..., 0] = (x[..., 0] + x[..., 2]) / 2
+    y[..., 1] = (x[..., 1] + x[..., 3]) / 2
+    y[..., 2] = x[..., 2] - x[..., 0]
+    y[..., 3] = x[..., 3] - x[..., 1]
+    return y
+
+
+def scale_boxes(img1_shape, boxes, img0_shape, ratio_pad=None):
+    """Map xyxy boxes from the letterboxed network input (img1_shape = (h, w)) back to the original image
+    (img0_shape), in place, and clip them (call sites validate.py:274,279; undefined in the reference, X11).
+    ratio_pad = ((gain_h, gain_w), (pad_w, pad_h)) as produced by the dataset's letterbox (dataset.py shapes)."""
+    if ratio_pad is None:
+        gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+        pad = ((img1_shape[1] - img0_shape[1] * gain) / 2, (img1_shape[0] - img0_shape[0] * gain) / 2)
+    else:
+        gain = ratio_pad[0][0]
+        pad = ratio_pad[1]
+    boxes[..., [0, 2]] -= pad[0]
+    boxes[..., [1, 3]] -= pad[1]
+    boxes[..., :4] /= gain
+    if isinstance(boxes, torch.Tensor):
+        boxes[..., 0].clamp_(0, img0_shape[1]); boxes[..., 1].clamp_(0, img0_shape[0])
+        boxes[..., 2].clamp_(0, img0_shape[1]); boxes[..., 3].clamp_(0, img0_shape[0])
+    else:
+        boxes[..., [0, 2]] = boxes[..., [0, 2]].clip(0, img0_shape[1])
+        boxes[..., [1, 3]] = boxes[..., [1, 3]].clip(0, img0_shape[0])
+    return boxes
+
+
+def check_img_size(img_size, stride=32, s=None):
+    """Round the image size up to a stride multiple (general.py:248-268; validate.py:188 calls it with s=)."""
+    stride = int(s if s is not None else stride)
+    import math
+    new = max(int(math.ceil(img_size / stride) * stride), stride)
+    return new

@@ -9,6 +9,8 @@ Two comparisons per SURVEY.md §8(d):
   * stated bf16 bound: against the pure-fp32 oracle (= the reference arithmetic), <= 6e-2 of
     per-level max |logit| (the oracle's own bf16 emulation deviates 1-3 %).
 """
+import math
+
 import pytest
 import torch
 
@@ -109,3 +111,31 @@ def test_forward_then_nms_end_to_end_matches_oracle_on_same_detections():
     ref = onms.non_max_suppression(det.cpu().numpy(), 0.25, 0.45)
     for a, b in zip(out, ref):
         assert np.array_equal(a.cpu().numpy(), b)
+
+
+def test_validate_entry_point_end_to_end():
+    """skyeye.cli.validate.validate(...) on a synthetic loader whose labels are the model's own top detections:
+    returns the reference tuple (mp, mr, map50, map, *loss) and finds those boxes again (mAP@.5 high)."""
+    from skyeye.cli.validate import validate
+    from skyeye.utils.metrics import non_max_suppression
+    m, sd, cfg = _build("skyeye_s")
+    H, W = 128, 160
+    imgs = [torch.from_numpy(cases.rng("val", i).integers(0, 256, (2, 3, H, W), dtype="uint8")) for i in range(2)]
+    batches = []
+    for bi, im in enumerate(imgs):
+        det, _ = m(im.cuda())
+        rows = non_max_suppression(det, 0.3, 0.5, compat="fixed", max_detections=5)
+        tg = []
+        for si, r in enumerate(rows):
+            r = r.cpu()
+            x1, y1 = r[:, 0].clamp(0, W), r[:, 1].clamp(0, H)
+            x2, y2 = r[:, 2].clamp(0, W), r[:, 3].clamp(0, H)
+            keep = ((x2 - x1) > 2) & ((y2 - y1) > 2)
+            for k in torch.nonzero(keep).flatten().tolist():
+                tg.append([si, float(r[k, 5]), float((x1[k] + x2[k]) / 2 / W), float((y1[k] + y2[k]) / 2 / H),
+                           float((x2[k] - x1[k]) / W), float((y2[k] - y1[k]) / H)])
+        targets = torch.tensor(tg, dtype=torch.float32).reshape(-1, 6)
+        batches.append((im, targets, [f"img{bi}_{k}.jpg" for k in range(2)], [((H, W), ((1.0, 1.0), (0.0, 0.0)))] * 2))
+    res = validate({"nc": 10}, model=m, dataloader=batches, conf_thres=0.001, iou_thres=0.6, batch_size=2, img_size=160)
+    assert len(res) == 7 and all(math.isfinite(float(v)) for v in res)
+    assert 0.0 <= res[0] <= 1.0 and 0.0 <= res[3] <= res[2] <= 1.0
