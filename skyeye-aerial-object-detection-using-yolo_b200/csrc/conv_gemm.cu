@@ -21,7 +21,8 @@
 //   sub-tiles (64 bf16 / 32 fp32 channels x 128 pixels) that one elected thread drains with TMA stores
 //   (coalesced, asynchronous, edge clipping for free) into a channel slice of the destination buffer.
 //   The residual sub-tile is TMA-prefetched into the same ring slot one sub-tile ahead and updated in
-//   place.  (The two 2x-upsampling lateral convs keep a direct replicated-store epilogue.)
+//   place.  The two 2x-upsampling lateral convs store the same sub-tile through four tensor maps, one per
+//   (dy, dx) phase of the upsampled image.
 // * Tile index -> (n-block, w, h, n) uses multiply-shift division: three runtime integer divisions per
 //   tile were ~800 cycles of serial latency on every role.
 // * K chunk = one swizzle span: 64 channels (SWIZZLE_128B), 32 (64B) or 16 (32B; the Focus conv).
@@ -157,7 +158,9 @@ __device__ __forceinline__ void epi_chunk_f32(const uint32_t* v, uint32_t bias_a
 template <int BN, int BK, int NCTA>
 __global__ void __launch_bounds__(352, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const ConvParams p) {
+                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
+                 const __grid_constant__ CUtensorMap tmU1, const __grid_constant__ CUtensorMap tmU2,
+                 const __grid_constant__ CUtensorMap tmU3, const ConvParams p) {
     using Cfg = ConvCfg<BN, BK, NCTA>;
     // NCTA == 2: the two CTAs of a cluster form a tcgen05 CTA pair.  One MMA (issued by the leader) computes
     // a 256 x BN tile: each CTA stages ITS 128 pixels and HALF of the weight tile, so the shared-memory
@@ -336,162 +339,97 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         };
 
-        if (!p.up2) {
-            auto n_sub = [&](int nb) {
-                int nv = (p.cout - nb * BN + sub_cols - 1) / sub_cols;
-                return nv < 0 ? 0 : (nv > BN / sub_cols ? BN / sub_cols : nv);
-            };
-            auto load_bias = [&](int nb) {
-                for (int i = tg; i < BN; i += GT) sts32f(sbias_g + 4u * i, __ldg(p.bias + nb * BN + i));
-            };
-            if (p.n_blocks == 1) load_bias(0);
-            if (T0 && p.has_res && tile < p.total_tiles) {  // residual of the very first sub-tile
-                int nb, w0, h0, n0;
-                decode_tile<NCTA>(p, tile, cta_rank, nb, w0, h0, n0);
-                if (n_sub(nb) > 0) {
-                    mbar_expect_tx(res_full(g * NB), (uint32_t)p.epi_box_bytes);
-                    tma_load_4d(ebuf_g, &tmR, res_full(g * NB), nb * BN, w0, h0, n0);
-                }
+        auto n_sub = [&](int nb) {
+            int nv = (p.cout - nb * BN + sub_cols - 1) / sub_cols;
+            return nv < 0 ? 0 : (nv > BN / sub_cols ? BN / sub_cols : nv);
+        };
+        auto load_bias = [&](int nb) {
+            for (int i = tg; i < BN; i += GT) sts32f(sbias_g + 4u * i, __ldg(p.bias + nb * BN + i));
+        };
+        if (p.n_blocks == 1) load_bias(0);
+        if (T0 && p.has_res && tile < p.total_tiles) {  // residual of the very first sub-tile
+            int nb, w0, h0, n0;
+            decode_tile<NCTA>(p, tile, cta_rank, nb, w0, h0, n0);
+            if (n_sub(nb) > 0) {
+                mbar_expect_tx(res_full(g * NB), (uint32_t)p.epi_box_bytes);
+                tma_load_4d(ebuf_g, &tmR, res_full(g * NB), nb * BN, w0, h0, n0);
             }
-            named_bar_sync(barid, GT);
-            for (; tile < p.total_tiles; tile += step) {
-                int nb, w0, h0, n0;
-                decode_tile<NCTA>(p, tile, cta_rank, nb, w0, h0, n0);
-                const int ncol0 = nb * BN;
-                const int nvalid = n_sub(nb);
-                if (T0 && g == 0) SKB_TR(2, 100);
-                if (p.n_blocks > 1) {  // the previous tile's last barrier ordered every read of the old bias
-                    load_bias(nb);
-                    named_bar_sync(barid, GT);
-                }
-                mbar_wait(tfull(g), aphase);
-                tc_fence_after();
-                if (T0 && g == 0) SKB_TR(2, 103);
-                for (int sub = 0; sub < nvalid; ++sub, ++qseq) {
-                    const uint32_t slot_i = qseq % NB;
-                    const uint32_t buf = ebuf_g + slot_i * Cfg::EPI_BUF;
-                    const int c0 = sub * sub_cols;
-                    const uint32_t rowp = buf + row_off;
-                    const bool last = sub == nvalid - 1;
-                    if (p.has_res) mbar_wait(res_full(g * NB + slot_i), (qseq / NB) & 1u);
-                    if (!p.out_f32) {
-                        const int pieces = sub_cols >> 5;  // 32 accumulator columns = 4 chunks of 8 bf16
-                        for (int hh = 0; hh < pieces; ++hh) {
-                            uint32_t v[32];
-                            tmem_ld32(acc + (uint32_t)(c0 + hh * 32), v);
-                            tmem_ld_wait();
-                            if (last && hh == pieces - 1) release_tmem();  // accumulator fully read: hand the TMEM stage back
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                epi_chunk_bf16(v + j * 8, sbias_g + 4u * (uint32_t)(c0 + hh * 32 + j * 8), p.act, p.has_res != 0,
-                                               rowp + ((((uint32_t)(hh * 4 + j)) ^ sw) << 4));
-                        }
-                    } else {  // fp32 store: 32 columns per sub-tile = 8 chunks of 4 floats
+        }
+        named_bar_sync(barid, GT);
+        for (; tile < p.total_tiles; tile += step) {
+            int nb, w0, h0, n0;
+            decode_tile<NCTA>(p, tile, cta_rank, nb, w0, h0, n0);
+            const int ncol0 = nb * BN;
+            const int nvalid = n_sub(nb);
+            if (T0 && g == 0) SKB_TR(2, 100);
+            if (p.n_blocks > 1) {  // the previous tile's last barrier ordered every read of the old bias
+                load_bias(nb);
+                named_bar_sync(barid, GT);
+            }
+            mbar_wait(tfull(g), aphase);
+            tc_fence_after();
+            if (T0 && g == 0) SKB_TR(2, 103);
+            for (int sub = 0; sub < nvalid; ++sub, ++qseq) {
+                const uint32_t slot_i = qseq % NB;
+                const uint32_t buf = ebuf_g + slot_i * Cfg::EPI_BUF;
+                const int c0 = sub * sub_cols;
+                const uint32_t rowp = buf + row_off;
+                const bool last = sub == nvalid - 1;
+                if (p.has_res) mbar_wait(res_full(g * NB + slot_i), (qseq / NB) & 1u);
+                if (!p.out_f32) {
+                    const int pieces = sub_cols >> 5;  // 32 accumulator columns = 4 chunks of 8 bf16
+                    for (int hh = 0; hh < pieces; ++hh) {
                         uint32_t v[32];
-                        tmem_ld32(acc + (uint32_t)c0, v);
+                        tmem_ld32(acc + (uint32_t)(c0 + hh * 32), v);
                         tmem_ld_wait();
-                        if (last) release_tmem();
+                        if (last && hh == pieces - 1) release_tmem();  // accumulator fully read: hand the TMEM stage back
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            epi_chunk_f32(v + j * 4, sbias_g + 4u * (uint32_t)(c0 + j * 4), p.act, rowp + ((((uint32_t)j) ^ sw) << 4));
+                        for (int j = 0; j < 4; ++j)
+                            epi_chunk_bf16(v + j * 8, sbias_g + 4u * (uint32_t)(c0 + hh * 32 + j * 8), p.act, p.has_res != 0,
+                                           rowp + ((((uint32_t)(hh * 4 + j)) ^ sw) << 4));
                     }
-                    if (T0) tma_store_wait_read<0>();  // the group's previous store has drained the OTHER slot
-                    fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the TMA engine
-                    named_bar_sync(barid, GT);
-                    if (T0) {
-                        tma_store_4d(&tmY, buf, ncol0 + c0, w0, h0, n0);
-                        tma_store_commit();
-                        if (g == 0) SKB_TR(2, 110);
-                        if (p.has_res) {  // prefetch the residual of the group's next sub-tile into the other slot
-                            const uint32_t s2 = (qseq + 1) % NB;
-                            int nb2 = nb, w2 = w0, h2 = h0, n2 = n0, c2 = c0 + sub_cols;
-                            bool have = !last;
-                            if (last && tile + step < p.total_tiles) {
-                                decode_tile<NCTA>(p, tile + step, cta_rank, nb2, w2, h2, n2);
-                                c2 = 0;
-                                have = n_sub(nb2) > 0;
-                            }
-                            if (have) {
-                                mbar_expect_tx(res_full(g * NB + s2), (uint32_t)p.epi_box_bytes);
-                                tma_load_4d(ebuf_g + s2 * Cfg::EPI_BUF, &tmR, res_full(g * NB + s2), nb2 * BN + c2, w2, h2, n2);
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
-                if (nvalid == 0) release_tmem();
-                aphase ^= 1;
-            }
-            if (T0) tma_store_wait_all();
-        } else {
-            // ------------- direct replicated stores (2x nearest upsample fused) -------------
-            const int hw = p.th * p.tw;
-            const int nl = m / hw;
-            const int rem = m - nl * hw;
-            const int hl = rem / p.tw;
-            const int wl = rem - hl * p.tw;
-            const bool row_in_box = m < p.tn * hw;
-            for (; tile < p.total_tiles; tile += step) {
-                int nb, w0, h0, n0;
-                decode_tile<NCTA>(p, tile, cta_rank, nb, w0, h0, n0);
-                const int ncol0 = nb * BN;
-                const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
-                const bool valid = row_in_box && n < p.B && h < p.Ho && w < p.Wo;
-                const size_t opix = ((size_t)n * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w;
-                mbar_wait(tfull(g), aphase);
-                tc_fence_after();
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                } else {  // fp32 store: 32 columns per sub-tile = 8 chunks of 4 floats
                     uint32_t v[32];
                     tmem_ld32(acc + (uint32_t)c0, v);
                     tmem_ld_wait();
-                    if (c0 + 32 >= BN) release_tmem();
-                    const int ncol = ncol0 + c0;
-                    if (valid) {
+                    if (last) release_tmem();
 #pragma unroll
-                        for (int gg = 0; gg < 4; ++gg) {
-                            const int col = ncol + gg * 8;
-                            if (col < p.cout) {
-                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-                                float f[8];
-                                f[0] = __uint_as_float(v[gg * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[gg * 8 + 1]) + b0.y;
-                                f[2] = __uint_as_float(v[gg * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[gg * 8 + 3]) + b0.w;
-                                f[4] = __uint_as_float(v[gg * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[gg * 8 + 5]) + b1.y;
-                                f[6] = __uint_as_float(v[gg * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[gg * 8 + 7]) + b1.w;
-                                if (p.act == SKB_ACT_SILU) {
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
-                                } else if (p.act == SKB_ACT_RELU) {
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
-                                }
-                                const size_t dx = (size_t)p.out_pitch, dy = (size_t)(2 * p.Wo) * p.out_pitch;
-                                if (p.out_f32) {
-                                    float* o = reinterpret_cast<float*>(p.out) + opix * p.out_pitch + col;
-                                    const float4 o0 = make_float4(f[0], f[1], f[2], f[3]);
-                                    const float4 o1 = make_float4(f[4], f[5], f[6], f[7]);
-                                    *reinterpret_cast<float4*>(o) = o0; *reinterpret_cast<float4*>(o + 4) = o1;
-                                    *reinterpret_cast<float4*>(o + dx) = o0; *reinterpret_cast<float4*>(o + dx + 4) = o1;
-                                    *reinterpret_cast<float4*>(o + dy) = o0; *reinterpret_cast<float4*>(o + dy + 4) = o1;
-                                    *reinterpret_cast<float4*>(o + dy + dx) = o0; *reinterpret_cast<float4*>(o + dy + dx + 4) = o1;
-                                } else {
-                                    uint4 o4;
-                                    o4.x = pack_bf16x2(f[0], f[1]); o4.y = pack_bf16x2(f[2], f[3]);
-                                    o4.z = pack_bf16x2(f[4], f[5]); o4.w = pack_bf16x2(f[6], f[7]);
-                                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_pitch + col;
-                                    *reinterpret_cast<uint4*>(o) = o4;
-                                    *reinterpret_cast<uint4*>(o + dx) = o4;
-                                    *reinterpret_cast<uint4*>(o + dy) = o4;
-                                    *reinterpret_cast<uint4*>(o + dy + dx) = o4;
-                                }
-                            }
+                    for (int j = 0; j < 8; ++j)
+                        epi_chunk_f32(v + j * 4, sbias_g + 4u * (uint32_t)(c0 + j * 4), p.act, rowp + ((((uint32_t)j) ^ sw) << 4));
+                }
+                if (T0) tma_store_wait_read<0>();  // the group's previous store has drained the OTHER slot
+                fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the TMA engine
+                named_bar_sync(barid, GT);
+                if (T0) {
+                    tma_store_4d(&tmY, buf, ncol0 + c0, w0, h0, n0);
+                    if (p.up2) {  // nearest 2x upsample (detector.py:214,218): the same sub-tile goes to all 4 phases
+                        tma_store_4d(&tmU1, buf, ncol0 + c0, w0, h0, n0);
+                        tma_store_4d(&tmU2, buf, ncol0 + c0, w0, h0, n0);
+                        tma_store_4d(&tmU3, buf, ncol0 + c0, w0, h0, n0);
+                    }
+                    tma_store_commit();
+                    if (g == 0) SKB_TR(2, 110);
+                    if (p.has_res) {  // prefetch the residual of the group's next sub-tile into the other slot
+                        const uint32_t s2 = (qseq + 1) % NB;
+                        int nb2 = nb, w2 = w0, h2 = h0, n2 = n0, c2 = c0 + sub_cols;
+                        bool have = !last;
+                        if (last && tile + step < p.total_tiles) {
+                            decode_tile<NCTA>(p, tile + step, cta_rank, nb2, w2, h2, n2);
+                            c2 = 0;
+                            have = n_sub(nb2) > 0;
+                        }
+                        if (have) {
+                            mbar_expect_tx(res_full(g * NB + s2), (uint32_t)p.epi_box_bytes);
+                            tma_load_4d(ebuf_g + s2 * Cfg::EPI_BUF, &tmR, res_full(g * NB + s2), nb2 * BN + c2, w2, h2, n2);
                         }
                     }
                 }
-                aphase ^= 1;
+                __syncwarp();
             }
+            if (nvalid == 0) release_tmem();
+            aphase ^= 1;
         }
+        if (T0) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -800,8 +738,11 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 // ---------------------------------------------------------------------------------------------
 template <int BN, int BK, int NCTA>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR, ConvParams p,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const CUtensorMap* tmU = nullptr) {
     using Cfg = ConvCfg<BN, BK, NCTA>;
+    const CUtensorMap& u1 = tmU ? tmU[0] : tmY;
+    const CUtensorMap& u2 = tmU ? tmU[1] : tmY;
+    const CUtensorMap& u3 = tmU ? tmU[2] : tmY;
     static bool attr_set = false;
     if (!attr_set) {
         SKB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BK, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -822,7 +763,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SKB_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, BK, NCTA>, tmA, tmB, tmY, tmR, p));
+    SKB_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, BK, NCTA>, tmA, tmB, tmY, tmR, u1, u2, u3, p));
     return SKB_OK;
 }
 
@@ -1011,7 +952,7 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
     p.sub_cols = p.out_f32 ? 32 : (BN >= 64 ? 64 : 32);
     p.epi_box_bytes = p.tn * p.th * p.tw * 128;
 
-    CUtensorMap tmA, tmB, tmY, tmR;
+    CUtensorMap tmA, tmB, tmY, tmR, tmU[3];
     {
         const uint64_t pitchB = (uint64_t)x->pitch * 2;
         uint64_t dims[5], str[4];
@@ -1040,7 +981,16 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
             rc = encode_tensor_map(&tmY, y->ptr, esz, 4, yd, ys, yb, row_bytes == 128 ? 128 : 0);
             if (rc != SKB_OK) return rc;
         } else {
-            tmY = tmB;  // unused by the direct-store epilogue
+            // one map per (dy, dx) phase of the upsampled image: pixel (n, 2h+dy, 2w+dx) = base + phase offset
+            // + w * 2 pixels + h * 2 rows; extents are the conv's own (Wo, Ho, N), so edge clipping still works
+            const uint64_t pix = (uint64_t)y->pitch * esz, rowb = pix * y->w;
+            uint64_t ud[4] = {(uint64_t)y->c, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)y->n};
+            uint64_t us[3] = {2 * pix, 2 * rowb, rowb * y->h};
+            for (int ph = 0; ph < 4; ++ph) {
+                const uint8_t* basep = (const uint8_t*)y->ptr + (ph >> 1) * rowb + (ph & 1) * pix;
+                rc = encode_tensor_map(ph == 0 ? &tmY : &tmU[ph - 1], basep, esz, 4, ud, us, yb, row_bytes == 128 ? 128 : 0);
+                if (rc != SKB_OK) return rc;
+            }
         }
         if (residual) {
             uint64_t rd[4] = {(uint64_t)residual->c, (uint64_t)residual->w, (uint64_t)residual->h, (uint64_t)residual->n};
@@ -1055,7 +1005,7 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
     }
     cudaStream_t st = (cudaStream_t)stream;
 #define SKB_CONV_CASE(bn, bk, nc) \
-    if (BN == bn && BK == bk && NCTA == nc) return launch_conv<bn, bk, nc>(tmA, tmB, tmY, tmR, p, st);
+    if (BN == bn && BK == bk && NCTA == nc) return launch_conv<bn, bk, nc>(tmA, tmB, tmY, tmR, p, st, upsample2x ? tmU : nullptr);
     SKB_CONV_CASE(256, 64, 1) SKB_CONV_CASE(128, 64, 1) SKB_CONV_CASE(64, 64, 1) SKB_CONV_CASE(32, 64, 1)
     SKB_CONV_CASE(256, 32, 1) SKB_CONV_CASE(128, 32, 1) SKB_CONV_CASE(64, 32, 1) SKB_CONV_CASE(32, 32, 1)
     SKB_CONV_CASE(256, 16, 1) SKB_CONV_CASE(128, 16, 1) SKB_CONV_CASE(64, 16, 1) SKB_CONV_CASE(32, 16, 1)
