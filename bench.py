@@ -196,13 +196,38 @@ def run_b200(args):
         det, _ = model(x_dev)
         batched_nms_padded(det, CONF, IOU, max_detections=MAX_DET, out=nms_out, out_count=nms_cnt)
 
+    # End-to-end step: every step copies ITS input batch from pinned host memory and reads ITS result back.
+    # Like any input pipeline, the H2D copy of step i+1 is enqueued on a copy stream before step i's result is
+    # awaited, so it overlaps step i's kernels (two device-side input buffers).
+    copy_stream = torch.cuda.Stream()
+    xbuf = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    state = {"i": 0, "primed": False}
+
+    def enqueue_h2d(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])    # the forward pass that last read this buffer has finished
+            xbuf[slot].copy_(host, non_blocking=True)  # H2D of one step's uint8 images from pinned memory
+            ready[slot].record(copy_stream)
+
     def step_e2e():
-        xd = host.to(dev, non_blocking=True)          # H2D of this step's uint8 images from pinned memory
-        det, _ = model(xd)                            # public API call (validate.py:245)
+        cur = state["i"] & 1
+        if not state["primed"]:
+            for sl in (0, 1):
+                consumed[sl].record()
+            enqueue_h2d(cur)
+            state["primed"] = True
+        main = torch.cuda.current_stream()
+        main.wait_event(ready[cur])
+        det, _ = model(xbuf[cur])                     # public API call (validate.py:245)
+        consumed[cur].record(main)
+        enqueue_h2d(cur ^ 1)                          # next step's input, overlapping this step's kernels
         batched_nms_padded(det, CONF, IOU, max_detections=MAX_DET, out=nms_out, out_count=nms_cnt)  # (validate.py:255)
         out_host.copy_(nms_out, non_blocking=True)    # D2H of the step's result
         cnt_host.copy_(nms_cnt, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        main.synchronize()
+        state["i"] += 1
 
     def barrier():
         if world > 1:
