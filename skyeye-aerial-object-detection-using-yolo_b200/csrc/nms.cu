@@ -113,8 +113,8 @@ static size_t nms_layout(int n, void* base, NmsWs* ws) {
 constexpr int KEY_SLOT_BITS = 22;
 constexpr int KEY_IMG_BITS = 10;
 constexpr int MAX_NMS_BOXES = 30000;  // metrics.py:393
-constexpr int NMS_THREADS = 256;
-constexpr int NMS_MAX_KEEP = 1536;
+constexpr int NMS_THREADS = 512;
+constexpr int NMS_MAX_KEEP = 1024;
 
 struct FilterParams {
     const float* pred;
