@@ -1,5 +1,6 @@
 // Library plumbing: version, thread-local error string, device check, TMA tensor-map encoding.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -45,6 +46,15 @@ int check_device() {
 }
 
 int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+
+int pdl_enabled() {  // tuning knob (not part of the ABI): SKB_PDL=0 launches every kernel fully serialised
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SKB_PDL");
+        v = e ? (atoi(e) != 0) : 1;
+    }
+    return v;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -45,6 +45,8 @@ int check_device();  // SKB_OK or SKB_ERR_ARCH / SKB_ERR_CUDA (message set)
     } while (0)
 
 int num_sms();
+// launch attribute list for kernels that call pdl_wait(): programmatic stream serialization (PDL)
+int pdl_enabled();
 
 // TMA tensor map (bf16 / fp32 elements), rank 2..5, dims/strides innermost first.
 // strides_bytes has rank-1 entries (stride of dims 1..rank-1). swizzle_bytes in {0,32,64,128}.
@@ -248,6 +250,13 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, u
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+
+// ---- programmatic dependent launch: the next kernel's prologue overlaps this kernel's tail ----
+// pdl_wait(): block until the preceding kernel in the stream has completed and its writes are visible (no-op
+// when the kernel was launched without the programmatic-serialization attribute).  pdl_launch_dependents():
+// allow the following kernel to start launching its CTAs as this kernel's CTAs retire.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- CTA pairs (cta_group::2): cluster helpers, peer-barrier TMA loads, paired MMA ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {

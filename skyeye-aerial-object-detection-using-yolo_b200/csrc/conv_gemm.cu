@@ -221,6 +221,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *slot_ptr;
+    // Everything above (barrier init, TMEM allocation, descriptor prefetch) touched no global data and may have
+    // overlapped the previous kernel's tail; from here on its outputs are read.
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0 || warp == 10) {
         // ===================== TMA producers =====================
@@ -542,6 +546,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *slot_ptr;
+    pdl_launch_dependents();  // prologue done without touching global data: see conv_gemm_kernel
+    pdl_wait();
 
     if (warp == 0) {
         // ===================== halo producer =====================
@@ -728,8 +734,18 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
         attr_set = true;
     }
     const int grid = p.total_items < num_sms() ? p.total_items : num_sms();
-    conv3x3_halo_kernel<BN><<<grid, 352, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, p);
-    SKB_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(352);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    SKB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<BN>, tmA, tmB, tmY, tmR, p));
     return SKB_OK;
 }
 
@@ -756,13 +772,15 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     cfg.blockDim = dim3(352);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = NCTA;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     SKB_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, BK, NCTA>, tmA, tmB, tmY, tmR, u1, u2, u3, p));
     return SKB_OK;
 }
