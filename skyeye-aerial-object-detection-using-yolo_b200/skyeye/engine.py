@@ -101,8 +101,9 @@ class PackedConv:
     def concat(parts: Sequence["PackedConv"]) -> "PackedConv":
         """Stack several convs that read the same input along Cout (CSP cv1||cv2, CLA k||v)."""
         p0 = parts[0]
-        assert all(p.cin == p0.cin and p.k == p0.k and p.cout == p.cout_pad for p in parts[:-1]), \
-            "only the last part of a fused conv may have padded output channels"
+        assert all(p.cin == p0.cin and p.k == p0.k for p in parts), "fused convs must share input channels and kernel size"
+        # only the REAL output rows of every part are stacked (padding rows are re-created at the end), so the
+        # parts may have any channel count (skyeye_m: 48 + 48 -> 96 rows padded to 128)
         out = PackedConv.__new__(PackedConv)
         out.cin, out.k = p0.cin, p0.k
         out.cin_real = p0.cin_real

@@ -22,6 +22,7 @@ pytestmark = pytest.mark.gpu
 
 # Stated whole-network bf16 bounds (max |diff| / per-level max |logit|), measured on B200:
 #   plain CSP/PAN detector (skyeye_s)            0.7-1.1 %  -> bound 2.5e-2
+#   deeper CSP/PAN detector (skyeye_m)           1.8 % max, 1.3 % rms (its own bf16 emulation: 1.6 %) -> 3e-2 / 2e-2
 #   + cross-layer attention + transformer heads  2.5-8.2 % max, 0.8-1.8 % rms -> max bound 1.2e-1, rms bound 3e-2
 #     (softmax over image rows and N x N attention amplify bf16 rounding of their logits; the oracle's own
 #     bf16 emulation deviates 2.1-4.4 % max from fp32 on the same inputs.  The max is one outlier among
@@ -30,8 +31,8 @@ pytestmark = pytest.mark.gpu
 # 6e-7 in fp32-accumulate mode (scripts/probe_numerics.py), but every stored activation is re-rounded
 # to bf16 and a sub-ulp difference flips roundings (error sqrt(delta*ulp)), so any two bf16 pipelines
 # (this one, the emulating oracle, PyTorch autocast) sit at mutual distance ~ the bf16 noise floor.
-BOUND = {"skyeye_s": 2.5e-2, "skyeye_nano_l": 1.2e-1}
-RMS_BOUND = {"skyeye_s": 1e-2, "skyeye_nano_l": 3e-2}
+BOUND = {"skyeye_s": 2.5e-2, "skyeye_m": 3e-2, "skyeye_nano_l": 1.2e-1}
+RMS_BOUND = {"skyeye_s": 1e-2, "skyeye_m": 2e-2, "skyeye_nano_l": 3e-2}
 
 
 def _rms(a, b):
@@ -49,7 +50,7 @@ def _build(variant, seed=0):
 
 
 @pytest.mark.parametrize("variant,shape", [("skyeye_s", (2, 3, 128, 160)), ("skyeye_nano_l", (2, 3, 128, 128)),
-                                           ("skyeye_nano_l", (1, 3, 256, 192))])
+                                           ("skyeye_nano_l", (1, 3, 256, 192)), ("skyeye_m", (1, 3, 128, 128))])
 def test_model_matches_oracle(variant, shape):
     m, sd, cfg = _build(variant)
     x = cases.image(shape)
