@@ -22,6 +22,7 @@ pytestmark = pytest.mark.gpu
 
 # Stated whole-network bf16 bounds (max |diff| / per-level max |logit|), measured on B200:
 #   plain CSP/PAN detector (skyeye_s)            0.7-1.1 %  -> bound 2.5e-2
+#   skyeye_l itself (conditioned CLA logits, see _condition): 0.7-1.5 % max, 0.6-1.1 % rms -> 4e-2 / 2e-2
 #   deeper CSP/PAN detector (skyeye_m)           1.8 % max, 1.3 % rms (its own bf16 emulation: 1.6 %) -> 3e-2 / 2e-2
 #   + cross-layer attention + transformer heads  2.5-8.2 % max, 0.8-1.8 % rms -> max bound 1.2e-1, rms bound 3e-2
 #     (softmax over image rows and N x N attention amplify bf16 rounding of their logits; the oracle's own
@@ -31,8 +32,8 @@ pytestmark = pytest.mark.gpu
 # 6e-7 in fp32-accumulate mode (scripts/probe_numerics.py), but every stored activation is re-rounded
 # to bf16 and a sub-ulp difference flips roundings (error sqrt(delta*ulp)), so any two bf16 pipelines
 # (this one, the emulating oracle, PyTorch autocast) sit at mutual distance ~ the bf16 noise floor.
-BOUND = {"skyeye_s": 2.5e-2, "skyeye_m": 3e-2, "skyeye_nano_l": 1.2e-1}
-RMS_BOUND = {"skyeye_s": 1e-2, "skyeye_m": 2e-2, "skyeye_nano_l": 3e-2}
+BOUND = {"skyeye_s": 2.5e-2, "skyeye_m": 3e-2, "skyeye_nano_l": 1.2e-1, "skyeye_l": 4e-2}
+RMS_BOUND = {"skyeye_s": 1e-2, "skyeye_m": 2e-2, "skyeye_nano_l": 3e-2, "skyeye_l": 2e-2}
 
 
 def _rms(a, b):
@@ -40,17 +41,35 @@ def _rms(a, b):
     return float((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt())
 
 
+def _condition(sd, variant):
+    """skyeye_l at random init is ILL-CONDITIONED in the reference arithmetic itself: without trained BN
+    statistics the activations grow to ~1e5 through its 111 conv layers, the cross-layer-attention logits reach
+    ~1e10 and its softmax over image rows is an argmax that flips on a 0.4 % perturbation -- the oracle's own
+    bf16 emulation then sits 50-65 % away from its fp32 result (oracle-only experiment).  For the
+    whole-network test at skyeye_l's real channel counts the CLA query/key projections are scaled by 1e-5
+    (logits O(1)); everything else keeps the reference init.  The CLA kernel itself is tested unscaled in
+    test_gpu_ops.py."""
+    if variant != "skyeye_l":
+        return sd
+    out = dict(sd)
+    for k, v in sd.items():
+        if "cross_attention" in k and ("query_projection" in k or "key_projection" in k):
+            out[k] = v * 1e-5
+    return out
+
+
 def _build(variant, seed=0):
     from skyeye.core.detector import construct_model
     cfg = om.get_cfg(variant)
-    sd = om.make_state_dict(cfg, seed)
+    sd = _condition(om.make_state_dict(cfg, seed), variant)
     m = construct_model(f"{variant}.yaml")
     m.load_state_dict(sd, strict=True)
     return m.cuda().eval(), sd, cfg
 
 
 @pytest.mark.parametrize("variant,shape", [("skyeye_s", (2, 3, 128, 160)), ("skyeye_nano_l", (2, 3, 128, 128)),
-                                           ("skyeye_nano_l", (1, 3, 256, 192)), ("skyeye_m", (1, 3, 128, 128))])
+                                           ("skyeye_nano_l", (1, 3, 256, 192)), ("skyeye_m", (1, 3, 128, 128)),
+                                           ("skyeye_l", (1, 3, 160, 128))])  # the bench variant itself (C = 256/512/1024, 4/8/16 heads)
 def test_model_matches_oracle(variant, shape):
     m, sd, cfg = _build(variant)
     x = cases.image(shape)
@@ -67,9 +86,15 @@ def test_model_matches_oracle(variant, shape):
         assert ef < BOUND[variant], (i, ef)
         assert ee < BOUND[variant], (i, ee)
         assert _rms(a, f) < RMS_BOUND[variant], (i, _rms(a, f))
-    # decoded rows: fp32 decode of those logits (class/objectness columns are sigmoids in [0,1])
-    assert float((det[..., 4:].cpu() - d_f32[..., 4:]).abs().max()) < 0.25
-    assert _rms(det[..., 4:], d_f32[..., 4:]) < RMS_BOUND[variant]
+    # decoded rows: fp32 decode of those logits (class/objectness columns are sigmoids in [0,1]).  skyeye_l's
+    # random-init logits are ~1e5 (see _condition), every sigmoid is saturated at 0 or 1 and a 1 % logit error flips
+    # the ones near zero, so for it the decoded comparison is made on the sign pattern instead.
+    if variant != "skyeye_l":
+        assert float((det[..., 4:].cpu() - d_f32[..., 4:]).abs().max()) < 0.25
+        assert _rms(det[..., 4:], d_f32[..., 4:]) < RMS_BOUND[variant]
+    else:
+        flipped = ((det[..., 4:].cpu() > 0.5) != (d_f32[..., 4:] > 0.5)).float().mean()
+        assert float(flipped) < 2e-2, float(flipped)
 
 
 def test_uint8_input_equals_float_input_divided_by_255():
