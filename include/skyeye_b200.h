@@ -119,6 +119,15 @@ int skb_layernorm_bf16(const skb_view* x, const float* gamma, const float* beta,
  * on the channel axis); o: bf16 view [B,H,W,C]; head_dim must be 64. */
 int skb_flash_attn_bf16(const skb_view* qkv, const skb_view* o, int32_t heads, float scale, void* stream);
 
+/* WindowedSelfAttention core (attention.py:372-395; the class is unwired in the reference):
+ * per (window, head)  o = softmax(q * scale @ k^T + bias[head] (+ mask[window % n_mask])) @ v  for windows of
+ * n_tok <= 64 tokens.  qkv: bf16 view [n_windows, 1, n_tok, 3C] = the qkv Linear's output (q | k | v on the channel
+ * axis, head-major inside each); bias: fp32 [heads][n_tok][n_tok] = relative_position_bias_table gathered by
+ * relative_position_index; mask: fp32 [n_mask][n_tok][n_tok] or NULL; o: bf16 view [n_windows, 1, n_tok, C];
+ * head_dim = C / heads must be a multiple of 8 and <= 64. */
+int skb_window_attn_bf16(const skb_view* qkv, const float* bias, const float* mask, int32_t n_mask, const skb_view* o,
+                         int32_t heads, float scale, void* stream);
+
 /* ---- decode (DetectionHead.process_detections, detector.py:88-145) -----------------------------
  * raw[l]: fp32 view [B,h_l,w_l,>=na*no] (channel = a*no + o, the 1x1 head conv output); 16-byte aligned,
  *   pitch a multiple of 4 and >= na*no rounded up to 4 (rows are staged with 16-byte loads).

@@ -397,6 +397,37 @@ def decode(raws: Sequence[Tensor], input_hw, anchors=None) -> Tensor:
     return torch.cat(out, 1)
 
 
+def relative_position_index(window: int) -> Tensor:
+    """Pair-wise relative position index of a window (attention.py:340-350): [w*w, w*w] into the bias table."""
+    ys, xs = torch.meshgrid(torch.arange(window), torch.arange(window), indexing="ij")
+    coords = torch.stack((ys, xs)).flatten(1)                      # [2, w*w]
+    rel = (coords[:, :, None] - coords[:, None, :]).permute(1, 2, 0).contiguous()
+    rel[:, :, 0] += window - 1
+    rel[:, :, 1] += window - 1
+    rel[:, :, 0] *= 2 * window - 1
+    return rel.sum(-1)
+
+
+def windowed_self_attention(x, sd, p, window, heads, mask=None, ctx=FP32) -> Tensor:
+    """WindowedSelfAttention.forward (attention.py:358-399): x [B*nW, w*w, C] -> same shape.
+    qkv Linear -> per head softmax(q*scale @ k^T + bias[rel_idx] (+ mask[window])) @ v -> proj Linear."""
+    B_, N, C = x.shape
+    hd = C // heads
+    wq, wp = sd[p + ".qkv.weight"], sd[p + ".proj.weight"]
+    if ctx.emu:
+        wq, wp = bf16_round(wq), bf16_round(wp)
+    qkv = ctx.q(F.linear(ctx.q(x), wq, sd[p + ".qkv.bias"])).reshape(B_, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0] * (hd ** -0.5), qkv[1], qkv[2]
+    attn = q @ k.transpose(-2, -1)
+    bias = sd[p + ".relative_position_bias_table"][relative_position_index(window).view(-1)].view(N, N, heads)
+    attn = attn + bias.permute(2, 0, 1).unsqueeze(0)
+    if mask is not None:
+        nW = mask.shape[0]
+        attn = (attn.view(B_ // nW, nW, heads, N, N) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, N, N)
+    o = ctx.q((torch.softmax(attn, dim=-1) @ v).transpose(1, 2).reshape(B_, N, C))
+    return ctx.q(F.linear(o, wp, sd[p + ".proj.bias"]))
+
+
 def features(x, sd, cfg, ctx=FP32) -> List[Tensor]:
     """Everything before the detection head: [p3, p4, p5] level features."""
     cfg = get_cfg(cfg)

@@ -372,3 +372,117 @@ extern "C" int skb_flash_attn_bf16(const skb_view* qkv, const skb_view* o, int32
     SKB_LAUNCH_CHECK();
     return SKB_OK;
 }
+
+// =============================================================================================
+// WindowedSelfAttention core (attention.py:372-395): windows of <= 64 tokens, relative-position bias, optional
+// additive window mask.  One CTA per (window, head), one thread per query row; K and V of the window live in
+// shared memory as bf16 and every thread walks them with broadcast reads.  4*N^2*d flop per window-head is tiny
+// (N <= 64): the kernel is bound by reading qkv and writing o once, so no tensor-core path is needed here.
+// =============================================================================================
+namespace skb {
+
+template <int HD>
+__global__ void __launch_bounds__(64)
+window_attn_kernel(const __nv_bfloat16* __restrict__ qkv, long qpitch, const float* __restrict__ bias, const float* __restrict__ mask,
+                   int n_mask, __nv_bfloat16* __restrict__ out, long opitch, int N, int C, float scale) {
+    __shared__ __align__(16) __nv_bfloat16 sK[64 * HD];
+    __shared__ __align__(16) __nv_bfloat16 sV[64 * HD];
+    const int win = blockIdx.x, head = blockIdx.y, t = threadIdx.x;
+    const __nv_bfloat16* base = qkv + (long)win * N * qpitch + head * HD;
+    for (int i = t; i < N * (HD / 8); i += 64) {  // 16-byte pieces of the K and V rows of this head
+        const int r = i / (HD / 8), c = i - r * (HD / 8);
+        reinterpret_cast<uint4*>(sK)[i] = *reinterpret_cast<const uint4*>(base + (long)r * qpitch + C + c * 8);
+        reinterpret_cast<uint4*>(sV)[i] = *reinterpret_cast<const uint4*>(base + (long)r * qpitch + 2 * C + c * 8);
+    }
+    __syncthreads();
+    if (t >= N) return;
+    float q[HD];
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+        const uint4 u = *reinterpret_cast<const uint4*>(base + (long)t * qpitch + c * 8);
+        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { q[c * 8 + 2 * k] = bf16_lo(w4[k]) * scale; q[c * 8 + 2 * k + 1] = bf16_hi(w4[k]) * scale; }
+    }
+    const float* brow = bias + ((long)head * N + t) * N;
+    const float* mrow = mask ? mask + ((long)(win % n_mask) * N + t) * N : nullptr;
+    float s[64];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        float a = -INFINITY;
+        if (j < N) {
+            a = 0.f;
+            const uint4* kr = reinterpret_cast<const uint4*>(sK + j * HD);
+#pragma unroll
+            for (int c = 0; c < HD / 8; ++c) {
+                const uint4 u = kr[c];
+                a += q[c * 8 + 0] * bf16_lo(u.x) + q[c * 8 + 1] * bf16_hi(u.x) + q[c * 8 + 2] * bf16_lo(u.y) + q[c * 8 + 3] * bf16_hi(u.y) +
+                     q[c * 8 + 4] * bf16_lo(u.z) + q[c * 8 + 5] * bf16_hi(u.z) + q[c * 8 + 6] * bf16_lo(u.w) + q[c * 8 + 7] * bf16_hi(u.w);
+            }
+            a += brow[j];
+            if (mrow) a += mrow[j];
+        }
+        s[j] = a;
+        mx = fmaxf(mx, a);
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        s[j] = j < N ? expf(s[j] - mx) : 0.f;
+        l += s[j];
+    }
+    float o[HD];
+#pragma unroll
+    for (int c = 0; c < HD; ++c) o[c] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < 64; ++j) {
+        if (j < N) {
+            const float pj = s[j];
+            const uint4* vr = reinterpret_cast<const uint4*>(sV + j * HD);
+#pragma unroll
+            for (int c = 0; c < HD / 8; ++c) {
+                const uint4 u = vr[c];
+                o[c * 8 + 0] += pj * bf16_lo(u.x); o[c * 8 + 1] += pj * bf16_hi(u.x); o[c * 8 + 2] += pj * bf16_lo(u.y); o[c * 8 + 3] += pj * bf16_hi(u.y);
+                o[c * 8 + 4] += pj * bf16_lo(u.z); o[c * 8 + 5] += pj * bf16_hi(u.z); o[c * 8 + 6] += pj * bf16_lo(u.w); o[c * 8 + 7] += pj * bf16_hi(u.w);
+            }
+        }
+    }
+    const float inv = 1.0f / l;
+    __nv_bfloat16* dst = out + ((long)win * N + t) * opitch + head * HD;
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+        uint4 u;
+        u.x = pack_bf16x2(o[c * 8 + 0] * inv, o[c * 8 + 1] * inv); u.y = pack_bf16x2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
+        u.z = pack_bf16x2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv); u.w = pack_bf16x2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + c * 8) = u;
+    }
+}
+
+}  // namespace skb
+
+extern "C" int skb_window_attn_bf16(const skb_view* qkv, const float* bias, const float* mask, int32_t n_mask, const skb_view* o,
+                                    int32_t heads, float scale, void* stream) {
+    int rc = check_device();
+    if (rc != SKB_OK) return rc;
+    SKB_REQUIRE(qkv && o && bias && qkv->ptr && o->ptr && qkv->dtype == SKB_BF16 && o->dtype == SKB_BF16, SKB_ERR_ARG, "window_attn: bad views");
+    const int C = o->c;
+    SKB_REQUIRE(heads >= 1 && qkv->c == 3 * C && C % heads == 0, SKB_ERR_ARG, "window_attn: C=%d heads=%d qkv channels=%d", C, heads, qkv->c);
+    const int hd = C / heads;
+    SKB_REQUIRE(hd == 16 || hd == 32 || hd == 64, SKB_ERR_UNSUPPORTED, "window_attn: head_dim %d (supported: 16, 32, 64)", hd);
+    SKB_REQUIRE(qkv->h == 1 && o->h == 1 && qkv->w == o->w && qkv->n == o->n && qkv->w >= 1 && qkv->w <= 64, SKB_ERR_UNSUPPORTED,
+                "window_attn: views must be [windows, 1, tokens <= 64, C] (got tokens %d)", qkv->w);
+    SKB_REQUIRE(qkv->pitch % 8 == 0 && o->pitch % 8 == 0 && ((uintptr_t)qkv->ptr & 15) == 0 && ((uintptr_t)o->ptr & 15) == 0, SKB_ERR_ARG,
+                "window_attn: alignment");
+    SKB_REQUIRE(!mask || n_mask >= 1, SKB_ERR_ARG, "window_attn: mask given with n_mask=%d", n_mask);
+    const int N = qkv->w;
+    dim3 grid(qkv->n, heads);
+    cudaStream_t st = (cudaStream_t)stream;
+    const __nv_bfloat16* qp = (const __nv_bfloat16*)qkv->ptr;
+    __nv_bfloat16* op = (__nv_bfloat16*)o->ptr;
+    if (hd == 64) window_attn_kernel<64><<<grid, 64, 0, st>>>(qp, qkv->pitch, bias, mask, n_mask, op, o->pitch, N, C, scale);
+    else if (hd == 32) window_attn_kernel<32><<<grid, 64, 0, st>>>(qp, qkv->pitch, bias, mask, n_mask, op, o->pitch, N, C, scale);
+    else window_attn_kernel<16><<<grid, 64, 0, st>>>(qp, qkv->pitch, bias, mask, n_mask, op, o->pitch, N, C, scale);
+    SKB_LAUNCH_CHECK();
+    return SKB_OK;
+}

@@ -145,3 +145,52 @@ class TransformerLayer(nn.Module):
 
     def forward(self, x):
         return L.run_module(self, x)
+
+
+class WindowedSelfAttention(nn.Module):
+    """Window attention with relative position bias (reference attention.py:312-399; the class is defined but
+    never instantiated there).  Same parameters and buffers (qkv, proj, relative_position_bias_table,
+    relative_position_index); forward(x [B*nW, w*w, C], mask [nW, w*w, w*w] | None) -> [B*nW, w*w, C].
+    qkv / proj are tcgen05 GEMMs, the per-window softmax(q k^T + bias + mask) v is skb_window_attn_bf16."""
+
+    def __init__(self, dim, window_size, num_heads):
+        super().__init__()
+        self.dim, self.window_size, self.num_heads = dim, window_size, num_heads
+        self.scale = (dim // num_heads) ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3)
+        self.proj = nn.Linear(dim, dim)
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * window_size - 1) ** 2, num_heads))
+        ys, xs = torch.meshgrid(torch.arange(window_size), torch.arange(window_size), indexing="ij")
+        coords = torch.stack((ys, xs)).flatten(1)
+        rel = (coords[:, :, None] - coords[:, None, :]).permute(1, 2, 0).contiguous()
+        rel[:, :, 0] += window_size - 1
+        rel[:, :, 1] += window_size - 1
+        rel[:, :, 0] *= 2 * window_size - 1
+        self.register_buffer("relative_position_index", rel.sum(-1))
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=0.02)
+
+    def lower(self, plan: Plan, x: View, mask: torch.Tensor = None, out: View = None, name="wsa") -> View:
+        """x: view [B*nW, 1, w*w, C]."""
+        dev, C, n_tok = plan.device, self.dim, self.window_size ** 2
+        assert x.h == 1 and x.w == n_tok and x.c == C, (x.h, x.w, x.c)
+        bias = self.relative_position_bias_table.detach().float()[self.relative_position_index.view(-1)]
+        bias = bias.view(n_tok, n_tok, self.num_heads).permute(2, 0, 1).contiguous().to(dev)
+        m = None if mask is None else mask.detach().float().contiguous().to(dev)
+        plan.keep += [bias, m]
+        qkv = plan.buf(x.n, 1, n_tok, 3 * C)
+        plan.conv(name + ".qkv", x, PackedConv(self.qkv.weight, self.qkv.bias, dev), qkv, 1, ACT_NONE)
+        o = plan.buf(x.n, 1, n_tok, C)
+        plan.add(name + ".attn", lambda s: L.E.window_attn(qkv, bias, m, o, self.num_heads, self.scale, s), "attention",
+                 4.0 * x.n * n_tok * n_tok * C, 2.0 * x.n * n_tok * 4 * C)
+        if out is None:
+            out = plan.buf(x.n, 1, n_tok, C)
+        return plan.conv(name + ".proj", o, PackedConv(self.proj.weight, self.proj.bias, dev), out, 1, ACT_NONE)
+
+    def forward(self, x, mask=None):
+        if not x.is_cuda:
+            raise RuntimeError("skyeye (B200) modules run on CUDA only; there is no CPU fallback")
+        plan = Plan(x.device)
+        xin = L.E.View(x.float().to(torch.bfloat16).unsqueeze(1).contiguous())
+        out = self.lower(plan, xin, mask)
+        plan.run()
+        return out.torch().squeeze(1).float()

@@ -188,6 +188,12 @@ def flash_attn(qkv: View, o: View, heads: int, scale: float, stream=None) -> Non
             "skb_flash_attn_bf16")
 
 
+def window_attn(qkv: View, bias: torch.Tensor, mask: Optional[torch.Tensor], o: View, heads: int, scale: float, stream=None) -> None:
+    N.check(N.lib().skb_window_attn_bf16(qkv.ref, bias.data_ptr(), mask.data_ptr() if mask is not None else None,
+                                         mask.shape[0] if mask is not None else 0, o.ref, heads, scale,
+                                         _stream_ptr() if stream is None else stream), "skb_window_attn_bf16")
+
+
 def decode(raws: Sequence[View], na: int, no: int, anchors, in_hw, det: torch.Tensor,
            raw_out: Optional[Sequence[torch.Tensor]] = None, stream=None) -> None:
     L = len(raws)

@@ -27,6 +27,10 @@ CLA_CASES = {"c32": (32, 64, 12, 10, 3), "c64": (64, 128, 8, 16, 4)}
 TL_CASES = {"c32h2": (32, 2, 6, 7, 5), "c128h2": (128, 2, 9, 8, 6)}
 
 
+# name -> (dim, window, heads, n_windows_total, n_mask_windows (0 = no mask), seed)
+WSA_CASES = {"c64w4h2": (64, 4, 2, 6, 0, 7), "c128w8h2": (128, 8, 2, 4, 0, 8), "c64w8h1_mask": (64, 8, 1, 6, 3, 9)}
+
+
 def _normal(key, shape, std):
     return torch.from_numpy((rng(*key).standard_normal(shape, dtype=np.float32) * std).astype(np.float32))
 
@@ -59,6 +63,25 @@ def tl_state(c, seed):
     sd["tl.norm1.weight"] = 1.0 + _normal(("tl", "n1w", seed), (c,), 0.1)
     sd["tl.norm2.weight"] = 1.0 + _normal(("tl", "n2w", seed), (c,), 0.1)
     return sd
+
+
+def wsa_state(dim, window, heads, seed):
+    """WindowedSelfAttention parameters (attention.py:333-357), reference key names under 'wsa.'."""
+    sd = {"wsa.qkv.weight": _normal(("wsaw", seed), (3 * dim, dim), 1 / math.sqrt(dim)),
+          "wsa.qkv.bias": _normal(("wsab", seed), (3 * dim,), 0.02),
+          "wsa.proj.weight": _normal(("wsapw", seed), (dim, dim), 1 / math.sqrt(dim)),
+          "wsa.proj.bias": _normal(("wsapb", seed), (dim,), 0.02),
+          "wsa.relative_position_bias_table": _normal(("wsat", seed), ((2 * window - 1) ** 2, heads), 0.5)}
+    return sd
+
+
+def wsa_inputs(dim, window, n_win, n_mask, seed):
+    x = _normal(("wsax", seed), (n_win, window * window, dim), 1.0)
+    mask = None
+    if n_mask:
+        m = rng("wsam", seed).random((n_mask, window * window, window * window)) < 0.2
+        mask = torch.from_numpy(np.where(m, -100.0, 0.0).astype(np.float32))  # Swin-style additive mask
+    return x, mask
 
 
 def tl_input(c, h, w, seed):

@@ -191,3 +191,22 @@ def test_decode_matches_oracle(hw):
     assert float((det.cpu() - ref).abs().max() / ref.abs().clamp_min(1.0).max()) < 1e-5
     for a, b_ in zip(raw_out, raws_ref):
         assert torch.equal(a.cpu(), b_)
+
+
+@pytest.mark.parametrize("name", list(cases.WSA_CASES) + ["c256w8h4"])
+def test_windowed_self_attention_matches_oracle(name):
+    """WindowedSelfAttention (attention.py:312-399) through the native lowering vs the CPU oracle on identical
+    bf16-representable inputs; includes a 64-token window with head_dim 64 and a masked case."""
+    from skyeye.core.models.attention import WindowedSelfAttention
+    dim, window, heads, n_win, n_mask, seed = cases.WSA_CASES.get(name, (256, 8, 4, 5, 0, 11))
+    sd = {k: (bf16r(v) if v.dim() == 2 and "table" not in k else v) for k, v in cases.wsa_state(dim, window, heads, seed).items()}
+    x, mask = cases.wsa_inputs(dim, window, n_win, n_mask, seed)
+    x = bf16r(x)
+    mod = WindowedSelfAttention(dim, window, heads)
+    mod.load_state_dict({k[len("wsa."):]: v for k, v in sd.items()}, strict=False)
+    mod = mod.cuda().eval()
+    got = mod(x.cuda(), None if mask is None else mask.cuda())
+    torch.cuda.synchronize()
+    ref = om.windowed_self_attention(x, sd, "wsa", window, heads, mask, om.Ctx("bf16"))
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < TOL

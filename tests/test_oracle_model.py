@@ -85,3 +85,14 @@ def test_live_reference_matches_oracle(variant):
     assert _rel(d2, det) < TOL
     for a, b in zip(r2, raws):
         assert _rel(a, b) < TOL
+
+
+@pytest.mark.parametrize("name", list(cases.WSA_CASES))
+def test_windowed_self_attention_matches_reference_golden(name, golden_dir):
+    """oracle.windowed_self_attention vs the reference class executed in the build container (attention.py:312-399)."""
+    dim, window, heads, n_win, n_mask, seed = cases.WSA_CASES[name]
+    x, mask = cases.wsa_inputs(dim, window, n_win, n_mask, seed)
+    y = om.windowed_self_attention(x, cases.wsa_state(dim, window, heads, seed), "wsa", window, heads, mask)
+    g = torch.from_numpy(np.load(os.path.join(golden_dir, f"wsa_{name}.npz"))["y"])
+    assert y.shape == g.shape
+    assert float((y - g).abs().max()) <= 2e-5 * float(g.abs().max())
