@@ -61,15 +61,10 @@ struct ConvParams {
     int tw, th, tn;
     int n_blocks, total_tiles;
     FastDiv fd_nb, fd_tw, fd_th;  // divisors n_blocks, tiles_w, tiles_h of the tile index decode
-    int B, Ho, Wo;
     int k_iters, cchunks;
     int a_box_bytes;
     int tap_dw[9], tap_dh[9], tap_ph[9], tap_coff[9];
-    void* out;
-    long long out_pitch;
     int out_f32, cout, up2;
-    const __nv_bfloat16* res;
-    long long res_pitch;
     const float* bias;
     int act;
     int has_res, sub_cols, epi_box_bytes;
@@ -943,7 +938,6 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
     p.n_blocks = cout_pad / BN;
     p.total_tiles = cdiv(m_tiles, NCTA) * p.n_blocks;  // work items: one per CTA, or per CTA pair
     p.fd_nb = make_fastdiv(p.n_blocks); p.fd_tw = make_fastdiv(p.tiles_w); p.fd_th = make_fastdiv(p.tiles_h);
-    p.B = x->n; p.Ho = Ho; p.Wo = Wo;
     p.cchunks = Cin / BK;
     p.k_iters = taps * p.cchunks;
     p.a_box_bytes = p.tn * p.th * p.tw * BK * 2;
@@ -960,9 +954,7 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
                 p.tap_dh[t] = 0; p.tap_dw[t] = 0; p.tap_ph[t] = 0; p.tap_coff[t] = 0;
             }
         }
-    p.out = y->ptr; p.out_pitch = y->pitch; p.out_f32 = y->dtype == SKB_F32; p.cout = y->c; p.up2 = upsample2x ? 1 : 0;
-    p.res = residual ? (const __nv_bfloat16*)residual->ptr : nullptr;
-    p.res_pitch = residual ? residual->pitch : 0;
+    p.out_f32 = y->dtype == SKB_F32; p.cout = y->c; p.up2 = upsample2x ? 1 : 0;
     p.bias = bias; p.act = act;
     p.trace = g_conv_trace;
     p.has_res = residual ? 1 : 0;
@@ -1076,11 +1068,10 @@ extern "C" int skb_focus_conv_bf16(const void* img, int32_t img_dtype, int32_t n
     p.n_blocks = cout_pad / BN;
     p.total_tiles = m_tiles * p.n_blocks;
     p.fd_nb = make_fastdiv(p.n_blocks); p.fd_tw = make_fastdiv(p.tiles_w); p.fd_th = make_fastdiv(p.tiles_h);
-    p.B = n; p.Ho = Ho; p.Wo = Wo;
     p.cchunks = 1; p.k_iters = 3;
     p.a_box_bytes = p.tn * p.th * p.tw * 64 * 2;
     for (int t = 0; t < 3; ++t) { p.tap_dh[t] = t - 1; p.tap_dw[t] = 0; p.tap_ph[t] = 0; p.tap_coff[t] = 0; }
-    p.out = y->ptr; p.out_pitch = y->pitch; p.out_f32 = 0; p.cout = y->c; p.up2 = 0;
+    p.out_f32 = 0; p.cout = y->c; p.up2 = 0;
     p.bias = bias; p.act = act; p.trace = g_conv_trace;
     p.sub_cols = BN >= 64 ? 64 : 32;
     const int row_bytes = p.sub_cols * 2;
