@@ -299,11 +299,22 @@ def run_b200(args):
     dom = max(("conv", "attention"), key=lambda k: table.get(k, {"ms_per_step": 0})["ms_per_step"])
     d = agg[dom]
     achieved = (d["flops"] / d["calls"]) / ((d["ms"] / d["calls"]) * 1e-3) / 1e12
+    traffic = None
+    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tj = json.load(f)
+        if dom == "attention" and args.variant == VARIANT and S == H and B == BATCH:
+            traffic = tj["flash_attn_kernel"]["dram_bytes_per_launch_avg"]
+    except Exception:
+        traffic = None
     roofline = {"bound": "tensor", "kernel": "flash_attn_kernel" if dom == "attention" else "conv_gemm_kernel",
                 "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
-                "traffic": None, "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                "traffic": traffic, "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_per_step": d["launches"] // nrep, "avg_launch_ms": d["ms"] / d["calls"],
-                "share_of_step": table[dom]["share"]}
+                "share_of_step": table[dom]["share"],
+                "algorithmic_flops_per_launch": d["flops"] / d["calls"], "algorithmic_bytes_per_launch": d["bytes"] / d["calls"],
+                "note": "attention at head_dim 64 is bound by the MUFU pipe (16 ex2/clk/SM measured, 256 flop per exponential): "
+                        "<= ~1.12 PFLOP/s at 1.85 GHz" if dom == "attention" else ""}
 
     # end-to-end through the public API with host buffers
     for _ in range(2):
