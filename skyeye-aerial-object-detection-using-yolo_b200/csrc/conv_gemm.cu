@@ -104,32 +104,54 @@ __device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int c
     w0 = iw * p.tw; h0 = ih * p.th; n0 = in * p.tn;
 }
 
-// bias + activation (+ residual) on 8 accumulator columns -> one 16-byte chunk of bf16
-__device__ __forceinline__ void epi_chunk_bf16(const uint32_t* v, uint32_t bias_addr, int act, bool has_res, uint32_t a16) {
-    const float4 b0 = lds128f(bias_addr), b1 = lds128f(bias_addr + 16u);
-    float2 x0 = fadd2(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(b0.x, b0.y));
-    float2 x1 = fadd2(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(b0.z, b0.w));
-    float2 x2 = fadd2(make_float2(__uint_as_float(v[4]), __uint_as_float(v[5])), make_float2(b1.x, b1.y));
-    float2 x3 = fadd2(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(b1.z, b1.w));
+// bias + activation (+ residual) on 32 accumulator columns -> four 16-byte chunks of bf16 in the staging row.
+// All shared-memory loads are issued first, then the 32 independent value chains, then the four stores: the
+// per-chunk version (load, compute, store, next chunk) was a serial ~100-cycle latency chain per chunk because the
+// volatile shared-memory accesses keep their program order (measured: ~2500 cycles per 128 x 64 sub-tile).
+__device__ __forceinline__ void epi_piece_bf16(const uint32_t* v, uint32_t bias_addr, int act, bool has_res, uint32_t rowp,
+                                               uint32_t chunk0, uint32_t sw) {
+    float4 b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = lds128f(bias_addr + 16u * i);
+    uint4 r[4];
+    uint32_t a16[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a16[j] = rowp + (((chunk0 + (uint32_t)j) ^ sw) << 4);
+    if (has_res) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] = lds128(a16[j]);
+    }
+    float2 x[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        x[2 * i] = fadd2(make_float2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), make_float2(b[i].x, b[i].y));
+        x[2 * i + 1] = fadd2(make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), make_float2(b[i].z, b[i].w));
+    }
     if (act == SKB_ACT_SILU) {
-        x0 = silu2_tanh(x0); x1 = silu2_tanh(x1); x2 = silu2_tanh(x2); x3 = silu2_tanh(x3);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = silu2_tanh(x[i]);
     } else if (act == SKB_ACT_RELU) {
-        x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f);
-        x2.x = fmaxf(x2.x, 0.f); x2.y = fmaxf(x2.y, 0.f); x3.x = fmaxf(x3.x, 0.f); x3.y = fmaxf(x3.y, 0.f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { x[i].x = fmaxf(x[i].x, 0.f); x[i].y = fmaxf(x[i].y, 0.f); }
     }
     if (has_res) {
-        const uint4 r = lds128(a16);
-        x0 = fadd2(x0, make_float2(bf16_lo(r.x), bf16_hi(r.x)));
-        x1 = fadd2(x1, make_float2(bf16_lo(r.y), bf16_hi(r.y)));
-        x2 = fadd2(x2, make_float2(bf16_lo(r.z), bf16_hi(r.z)));
-        x3 = fadd2(x3, make_float2(bf16_lo(r.w), bf16_hi(r.w)));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            x[4 * j + 0] = fadd2(x[4 * j + 0], make_float2(bf16_lo(r[j].x), bf16_hi(r[j].x)));
+            x[4 * j + 1] = fadd2(x[4 * j + 1], make_float2(bf16_lo(r[j].y), bf16_hi(r[j].y)));
+            x[4 * j + 2] = fadd2(x[4 * j + 2], make_float2(bf16_lo(r[j].z), bf16_hi(r[j].z)));
+            x[4 * j + 3] = fadd2(x[4 * j + 3], make_float2(bf16_lo(r[j].w), bf16_hi(r[j].w)));
+        }
     }
-    uint4 o4;
-    o4.x = pack_bf16x2(x0.x, x0.y);
-    o4.y = pack_bf16x2(x1.x, x1.y);
-    o4.z = pack_bf16x2(x2.x, x2.y);
-    o4.w = pack_bf16x2(x3.x, x3.y);
-    sts128(a16, o4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 o4;
+        o4.x = pack_bf16x2(x[4 * j + 0].x, x[4 * j + 0].y);
+        o4.y = pack_bf16x2(x[4 * j + 1].x, x[4 * j + 1].y);
+        o4.z = pack_bf16x2(x[4 * j + 2].x, x[4 * j + 2].y);
+        o4.w = pack_bf16x2(x[4 * j + 3].x, x[4 * j + 3].y);
+        sts128(a16[j], o4);
+    }
 }
 // bias + activation on 4 accumulator columns -> one 16-byte chunk of fp32 (precise SiLU)
 __device__ __forceinline__ void epi_chunk_f32(const uint32_t* v, uint32_t bias_addr, int act, uint32_t a16) {
@@ -377,16 +399,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (p.has_res) mbar_wait(res_full(g * NB + slot_i), (qseq / NB) & 1u);
                 if (!p.out_f32) {
                     const int pieces = sub_cols >> 5;  // 32 accumulator columns = 4 chunks of 8 bf16
-                    for (int hh = 0; hh < pieces; ++hh) {
-                        uint32_t v[32];
-                        tmem_ld32(acc + (uint32_t)(c0 + hh * 32), v);
+                    uint32_t v[64];
+                    {   // both 32-column pieces of the sub-tile are loaded from TMEM before any arithmetic starts
+                        uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+                        uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+                        tmem_ld32(acc + (uint32_t)c0, lo);
+                        if (pieces == 2) tmem_ld32(acc + (uint32_t)(c0 + 32), hi);
                         tmem_ld_wait();
-                        if (last && hh == pieces - 1) release_tmem();  // accumulator fully read: hand the TMEM stage back
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            epi_chunk_bf16(v + j * 8, sbias_g + 4u * (uint32_t)(c0 + hh * 32 + j * 8), p.act, p.has_res != 0,
-                                           rowp + ((((uint32_t)(hh * 4 + j)) ^ sw) << 4));
                     }
+                    if (last) release_tmem();  // accumulator fully read: hand the TMEM stage back
+                    epi_piece_bf16(v, sbias_g + 4u * (uint32_t)c0, p.act, p.has_res != 0, rowp, 0u, sw);
+                    if (pieces == 2) epi_piece_bf16(v + 32, sbias_g + 4u * (uint32_t)(c0 + 32), p.act, p.has_res != 0, rowp, 4u, sw);
                 } else {  // fp32 store: 32 columns per sub-tile = 8 chunks of 4 floats
                     uint32_t v[32];
                     tmem_ld32(acc + (uint32_t)c0, v);
@@ -668,20 +691,20 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint32_t rowp = bufa + row_off;
                 const bool last = sub == NSUB - 1;
                 if (p.has_res) mbar_wait(res_full(g * NB + slot_i), (qseq / NB) & 1u);
-#pragma unroll 1
-                for (int hh = 0; hh < 2; ++hh) {
-                    uint32_t v[32];
-                    tmem_ld32(acc + (uint32_t)(c0 + hh * 32), v);
+                {
+                    uint32_t v[64];
+                    uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+                    uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+                    tmem_ld32(acc + (uint32_t)c0, lo);
+                    tmem_ld32(acc + (uint32_t)(c0 + 32), hi);
                     tmem_ld_wait();
-                    if (last && hh == 1) {
+                    if (last) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty(buf));
                     }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        epi_chunk_bf16(v + j * 8, sbias_g + 4u * (uint32_t)(c0 + hh * 32 + j * 8), p.act, p.has_res != 0,
-                                       rowp + ((((uint32_t)(hh * 4 + j)) ^ sw) << 4));
+                    epi_piece_bf16(v, sbias_g + 4u * (uint32_t)c0, p.act, p.has_res != 0, rowp, 0u, sw);
+                    epi_piece_bf16(v + 32, sbias_g + 4u * (uint32_t)(c0 + 32), p.act, p.has_res != 0, rowp, 4u, sw);
                 }
                 if (NB == 2 && T0) tma_store_wait_read<0>();  // store(q-1) has drained the other slot
                 fence_proxy_async_smem();
