@@ -154,10 +154,12 @@ class ClockSampler:
             os.unlink(self.f.name)
         except OSError:
             pass
-        sm.sort()
-        med = sm[len(sm) // 2] if sm else None  # sampler runs only while the timed region does
-        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
-                "power_w_max": max(power) if power else None}
+        # samples under load = power draw at least half of the maximum seen (the sampler starts during warm-up)
+        pmax = max(power) if power else 0.0
+        loaded = sorted(c for c, w in zip(sm, power) if w >= 0.5 * pmax) or sorted(sm)
+        med = loaded[len(loaded) // 2] if loaded else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(loaded),
+                "power_w_max": pmax if power else None}
 
 
 def run_b200(args):
@@ -252,12 +254,21 @@ def run_b200(args):
         return ms
 
     warm = max(args.warmup, 3)
+    step_resident()  # builds the plan (weight packing, buffers, graph capture): not part of any sampled region
+    torch.cuda.synchronize()
+    # nvidia-smi needs a few hundred ms to deliver its first sample and the timed region can be shorter than that,
+    # so the sampler also covers the warm-up steps (same kernels, same load); idle samples are filtered in stop().
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        t_end = time.perf_counter() + 0.6
+        while time.perf_counter() < t_end:  # keep the GPU under the bench load until the sampler is running
+            step_resident()
+        torch.cuda.synchronize()
     for _ in range(warm):
         step_resident()
     torch.cuda.synchronize()
     plan = model.plan_for(x_dev)
 
-    sampler = ClockSampler(local) if rank == 0 else None
     ms_total = timed(step_resident, args.steps)
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps

@@ -33,7 +33,7 @@ constexpr int ATT_ONES_BYTES = ATT_BKV * 128;       // 8 KB of bf16 1.0: extra B
 constexpr int ATT_SMEM = ATT_Q_BYTES + 2 * ATT_KVS * ATT_KV_BYTES + ATT_ONES_BYTES + 1024 + 256;
 constexpr int ATT_ON = ATT_D + 16;                  // PV accumulator width: 64 output dims + 16 copies of sum_k P
 constexpr uint32_t ATT_TMEM_COLS = 256;             // S0/P0 [0,64) S1/P1 [64,128) O [128,208) Q [208,240)
-constexpr int ATT_POLY_DEFAULT = 0;                 // exponentials per 64 evaluated on the FMA pipes (0, 8, 16, 24, 32)
+constexpr int ATT_POLY_DEFAULT = 8;                 // exponentials per 64 evaluated on the FMA pipes (0, 8, 16, 24, 32)
 
 struct AttnParams {
     int N, heads, C, T;
