@@ -98,6 +98,15 @@ size_t skb_focus_conv_workspace_bytes(int32_t n, int32_t h, int32_t w);
 int skb_focus_conv_bf16(const void* img, int32_t img_dtype, int32_t n, int32_t h, int32_t w, const void* w_rowtap,
                         const float* bias, const skb_view* y, int32_t cout_pad, int32_t act, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* Inference-time pre-processing in one pass: `letterbox` (skyeye/core/data/augmentation.py:442-496:
+ * cv2.resize INTER_LINEAR to new_h x new_w, constant border `pad`) + BGR->RGB + HWC->CHW (detect.py:131-132).
+ * src: uint8 [h0][w0][3] BGR (device memory, row pitch src_pitch bytes); dst: uint8 [3][H][W] RGB planes (device) --
+ * the layout skb_focus_conv_bf16 / skb_focus_nchw_u8 consume.  The resized image occupies rows [top, top+new_h) and
+ * columns [left, left+new_w).  The bilinear resize is OpenCV's 8-bit fixed-point scheme (11-bit coefficients,
+ * (b0*(S0>>4)>>16 + b1*(S1>>4)>>16 + 2) >> 2): bit-exact with cv2.resize when down-scaling or copying; when
+ * up-scaling OpenCV's dispatched path differs by 1 LSB on < 0.5 % of the samples. */
+int skb_letterbox_u8(const uint8_t* src, int32_t h0, int32_t w0, int32_t src_pitch, uint8_t* dst, int32_t H, int32_t W,
+                     int32_t new_h, int32_t new_w, int32_t top, int32_t left, int32_t pad, void* stream);
 /* nn.MaxPool2d(5, stride 1, pad 2) (blocks.py:143-144); SPP's 9 and 13 pools are cascades of it. */
 int skb_maxpool5_bf16(const skb_view* x, const skb_view* y, void* stream);
 /* CombinedAttention = ChannelAttention + SpatialAttention (attention.py:37-60, 80-98, 118-130).

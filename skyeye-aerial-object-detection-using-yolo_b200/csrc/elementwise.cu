@@ -98,6 +98,58 @@ __global__ void focus_pad_kernel(const T* __restrict__ img, int N, int H, int W,
 }
 
 // ---------------------------------------------------------------------------------------------
+// letterbox + BGR->RGB + HWC->CHW (augmentation.py:442-496, detect.py:131-132), OpenCV's 8-bit INTER_LINEAR
+// ---------------------------------------------------------------------------------------------
+struct LinCoef {
+    int s0, s1, a0, a1;  // source indices and 11-bit fixed-point weights
+};
+// cv::resize INTER_LINEAR coefficient of destination index d: f = (float)((d + 0.5) * scale - 0.5), split into
+// floor + fraction, clamped at the borders, weights = cvRound((1 - f) * 2048), cvRound(f * 2048)
+__device__ __forceinline__ LinCoef lin_coef(int d, double scale, int n_src) {
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= (float)s;
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= n_src - 1) { f = 0.f; s = n_src - 1; }
+    LinCoef c;
+    c.s0 = s;
+    c.s1 = min(s + 1, n_src - 1);
+    c.a0 = __float2int_rn((1.0f - f) * 2048.0f);
+    c.a1 = __float2int_rn(f * 2048.0f);
+    return c;
+}
+__global__ void letterbox_kernel(const uint8_t* __restrict__ src, int h0, int w0, int pitch, uint8_t* __restrict__ dst, int H, int W,
+                                 int new_h, int new_w, int top, int left, int pad, double sx, double sy, int resize) {
+    const long total = (long)H * W;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W), y = (int)(i / W);
+        const int rx = x - left, ry = y - top;
+        int b = pad, g = pad, r = pad;
+        if (rx >= 0 && rx < new_w && ry >= 0 && ry < new_h) {
+            if (!resize) {
+                const uint8_t* px = src + (long)ry * pitch + rx * 3;
+                b = px[0]; g = px[1]; r = px[2];
+            } else {
+                const LinCoef cx = lin_coef(rx, sx, w0), cy = lin_coef(ry, sy, h0);
+                const uint8_t* r0 = src + (long)cy.s0 * pitch;
+                const uint8_t* r1 = src + (long)cy.s1 * pitch;
+                int out[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int h0v = r0[cx.s0 * 3 + c] * cx.a0 + r0[cx.s1 * 3 + c] * cx.a1;  // horizontal pass, x 2048
+                    const int h1v = r1[cx.s0 * 3 + c] * cx.a0 + r1[cx.s1 * 3 + c] * cx.a1;
+                    out[c] = (((cy.a0 * (h0v >> 4)) >> 16) + ((cy.a1 * (h1v >> 4)) >> 16) + 2) >> 2;
+                }
+                b = out[0]; g = out[1]; r = out[2];
+            }
+        }
+        dst[i] = (uint8_t)r;                 // RGB planes
+        dst[total + i] = (uint8_t)g;
+        dst[2 * total + i] = (uint8_t)b;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // MaxPool2d(5, 1, 2) on bf16 NHWC (padding acts as -inf)
 // ---------------------------------------------------------------------------------------------
 __global__ void maxpool5_kernel(const __nv_bfloat16* __restrict__ x, long xpitch, __nv_bfloat16* __restrict__ y, long ypitch,
@@ -513,6 +565,21 @@ int launch_focus_pad(const void* img, int img_dtype, int n, int h, int w, void* 
     return SKB_OK;
 }
 }  // namespace skb
+
+extern "C" int skb_letterbox_u8(const uint8_t* src, int32_t h0, int32_t w0, int32_t src_pitch, uint8_t* dst, int32_t H, int32_t W,
+                                int32_t new_h, int32_t new_w, int32_t top, int32_t left, int32_t pad, void* stream) {
+    int rc = check_device();
+    if (rc != SKB_OK) return rc;
+    SKB_REQUIRE(src && dst && h0 > 0 && w0 > 0 && H > 0 && W > 0 && new_h > 0 && new_w > 0, SKB_ERR_ARG, "letterbox: bad arguments");
+    SKB_REQUIRE(src_pitch >= 3 * w0 && top >= 0 && left >= 0 && top + new_h <= H && left + new_w <= W && pad >= 0 && pad <= 255, SKB_ERR_ARG,
+                "letterbox: resized image %dx%d at (%d,%d) does not fit %dx%d", new_h, new_w, top, left, H, W);
+    const int resize = (new_h != h0 || new_w != w0) ? 1 : 0;
+    const long total = (long)H * W;
+    letterbox_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, h0, w0, src_pitch, dst, H, W, new_h, new_w, top, left, pad,
+                                                                            (double)w0 / new_w, (double)h0 / new_h, resize);
+    SKB_LAUNCH_CHECK();
+    return SKB_OK;
+}
 
 extern "C" int skb_maxpool5_bf16(const skb_view* x, const skb_view* y, void* stream) {
     int rc = check_device();

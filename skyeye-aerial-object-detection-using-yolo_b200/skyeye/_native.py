@@ -88,6 +88,8 @@ _SIGNATURES = {
     "skb_focus_conv_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "skb_focus_conv_bf16": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, POINTER(skb_view),
                                       c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
+    "skb_letterbox_u8": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                   c_int32, c_void_p]),
     "skb_maxpool5_bf16": (c_int32, [POINTER(skb_view), POINTER(skb_view), c_void_p]),
     "skb_cbam_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "skb_cbam_bf16": (c_int32, [POINTER(skb_view), c_void_p, c_void_p, c_int32, c_void_p, POINTER(skb_view),

@@ -99,3 +99,31 @@ def check_img_size(img_size, stride=32, s=None):
     import math
     new = max(int(math.ceil(img_size / stride) * stride), stride)
     return new
+
+
+def letterbox_geometry(h: int, w: int, new_shape=640, stride: int = 32):
+    """Sizes of `letterbox` (augmentation.py:442-496 semantics as used by this package's host version above):
+    returns (H, W, new_h, new_w, top, left, ratio) of the padded output and the resized image inside it."""
+    if isinstance(new_shape, int):
+        new_shape = (new_shape, new_shape)
+    r = min(new_shape[0] / h, new_shape[1] / w)
+    nh, nw = int(round(h * r)), int(round(w * r))
+    ph, pw = (-nh) % stride, (-nw) % stride
+    return nh + ph, nw + pw, nh, nw, ph // 2, pw // 2, r
+
+
+def letterbox_gpu(img, new_shape=640, color: int = 114, stride: int = 32, out: "torch.Tensor" = None):
+    """letterbox + BGR->RGB + HWC->CHW on the GPU in one kernel (skb_letterbox_u8).  img: uint8 [h, w, 3] BGR, numpy or
+    torch (host or device).  Returns (uint8 CUDA tensor [3, H, W] RGB, ratio, (left, top)) -- ready for model(x[None])."""
+    from .. import _native as N
+    t = torch.from_numpy(np.ascontiguousarray(img)) if isinstance(img, np.ndarray) else img
+    assert t.dtype == torch.uint8 and t.dim() == 3 and t.shape[2] == 3, "expected a uint8 HWC BGR image"
+    t = t.contiguous().cuda(non_blocking=True)
+    h, w = int(t.shape[0]), int(t.shape[1])
+    H, W, nh, nw, top, left, r = letterbox_geometry(h, w, new_shape, stride)
+    if out is None:
+        out = torch.empty((3, H, W), dtype=torch.uint8, device=t.device)
+    assert out.shape == (3, H, W) and out.is_contiguous() and out.is_cuda
+    N.check(N.lib().skb_letterbox_u8(t.data_ptr(), h, w, 3 * w, out.data_ptr(), H, W, nh, nw, top, left, int(color),
+                                     torch.cuda.current_stream().cuda_stream), "skb_letterbox_u8")
+    return out, r, (left, top)

@@ -210,3 +210,25 @@ def test_windowed_self_attention_matches_oracle(name):
     ref = om.windowed_self_attention(x, sd, "wsa", window, heads, mask, om.Ctx("bf16"))
     assert got.shape == ref.shape
     assert rel_err(got, ref) < TOL
+
+
+@pytest.mark.parametrize("hw,new", [((100, 200), 128), ((720, 1280), 640), ((333, 517), 256), ((64, 96), 96), ((96, 128), 128),
+                                    ((50, 70), 160)])
+def test_letterbox_gpu_matches_cv2_pipeline(hw, new):
+    """skb_letterbox_u8 vs the host pipeline it replaces: cv2.resize(INTER_LINEAR) + copyMakeBorder(114) (letterbox,
+    augmentation.py:442-496) + BGR->RGB + HWC->CHW (detect.py:131-132).  Bit-exact when down-scaling or copying; when
+    up-scaling OpenCV's dispatched resize differs from its own fixed-point reference by 1 LSB on a few samples."""
+    cv2 = pytest.importorskip("cv2")
+    from skyeye.utils.general import letterbox, letterbox_gpu
+    img = cases.rng("lb", hw, new).integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8)
+    ref_hwc, r, (left, top) = letterbox(img, new)
+    ref = np.ascontiguousarray(ref_hwc[..., ::-1].transpose(2, 0, 1))
+    got, r2, (left2, top2) = letterbox_gpu(img, new)
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    assert got.shape == ref.shape and (left2, top2) == (left, top) and abs(r - r2) < 1e-12
+    diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+    if r <= 1.0:
+        assert int(diff.max()) == 0
+    else:
+        assert int(diff.max()) <= 1 and float((diff > 0).mean()) < 5e-3
