@@ -269,11 +269,11 @@ class SkyEyeDetector(nn.Module):
     @torch.no_grad()
     def predict(self, source, img_size=640, conf_thres=0.25, iou_thres=0.45, max_det=300) -> Results:
         """README-style call on image path(s) / HWC uint8 array(s): letterbox -> forward -> NMS."""
-        from ...utils.general import load_images
+        from ...utils.general import load_images_gpu
         from ...utils.metrics import non_max_suppression
         dev = next(self.parameters()).device
-        batch, files, origs = load_images(source, img_size)
-        det, _ = self.forward(batch.to(dev))
+        batch, files, origs = load_images_gpu(source, img_size, dev)  # letterbox + BGR->RGB + HWC->CHW on the GPU, uint8
+        det, _ = self.forward(batch)
         return Results(non_max_suppression(det, conf_thres, iou_thres, max_detections=max_det), origs, self.names, files)
 
 

@@ -127,3 +127,33 @@ def letterbox_gpu(img, new_shape=640, color: int = 114, stride: int = 32, out: "
     N.check(N.lib().skb_letterbox_u8(t.data_ptr(), h, w, 3 * w, out.data_ptr(), H, W, nh, nw, top, left, int(color),
                                      torch.cuda.current_stream().cuda_stream), "skb_letterbox_u8")
     return out, r, (left, top)
+
+
+def load_images_gpu(source, img_size=640, device="cuda"):
+    """Like load_images, with the letterbox / colour / layout conversion on the GPU: returns (uint8 CUDA tensor
+    [B,3,H,W] RGB -- the model scales by 1/255 in its first kernel --, names, originals).  Images whose letterboxed
+    sizes differ are padded (114) to the largest, as the host version does."""
+    import cv2
+    items = source if isinstance(source, (list, tuple)) else [source]
+    names, origs = [], []
+    for i, it in enumerate(items):
+        if isinstance(it, (str, Path)):
+            im = cv2.imread(str(it))
+            if im is None:
+                raise FileNotFoundError(it)
+            names.append(str(it))
+        else:
+            im = np.asarray(it)
+            names.append(f"image{i}.jpg")
+        origs.append(im)
+    geo = [letterbox_geometry(im.shape[0], im.shape[1], img_size) for im in origs]
+    H, W = max(g[0] for g in geo), max(g[1] for g in geo)
+    batch = torch.full((len(origs), 3, H, W), 114, dtype=torch.uint8, device=device)
+    with torch.cuda.device(batch.device):
+        for b, (im, g) in enumerate(zip(origs, geo)):
+            if (g[0], g[1]) == (H, W):
+                letterbox_gpu(im, img_size, out=batch[b])
+            else:  # smaller letterbox: top-left aligned inside the batch frame like the host version
+                t, _, _ = letterbox_gpu(im, img_size)
+                batch[b, :, : g[0], : g[1]] = t
+    return batch, names, origs

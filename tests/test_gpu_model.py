@@ -164,3 +164,18 @@ def test_validate_entry_point_end_to_end():
     res = validate({"nc": 10}, model=m, dataloader=batches, conf_thres=0.001, iou_thres=0.6, batch_size=2, img_size=160)
     assert len(res) == 7 and all(math.isfinite(float(v)) for v in res)
     assert 0.0 <= res[0] <= 1.0 and 0.0 <= res[3] <= res[2] <= 1.0
+
+
+def test_readme_style_call_uses_gpu_preprocessing():
+    """model(image) (README.md:46-53): GPU letterbox batch == host letterbox batch (down-scaling: bit-exact), and the
+    call returns a Results object with per-image detections."""
+    pytest.importorskip("cv2")
+    from skyeye.utils.general import load_images, load_images_gpu
+    m, sd, cfg = _build("skyeye_s")
+    imgs = [cases.rng("readme", i).integers(0, 256, (300 + 40 * i, 500, 3), dtype="uint8") for i in range(2)]
+    host, _, _ = load_images(imgs, 256)
+    dev, names, origs = load_images_gpu(imgs, 256)
+    assert dev.dtype == torch.uint8 and tuple(dev.shape) == tuple(host.shape)
+    assert torch.equal(dev.cpu().float() / 255.0, host)
+    res = m(imgs[0])
+    assert len(res) == 1 and res.pred[0].dim() == 2 and res.pred[0].shape[1] in (6, 7)
