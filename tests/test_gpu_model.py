@@ -179,3 +179,18 @@ def test_readme_style_call_uses_gpu_preprocessing():
     assert torch.equal(dev.cpu().float() / 255.0, host)
     res = m(imgs[0])
     assert len(res) == 1 and res.pred[0].dim() == 2 and res.pred[0].shape[1] in (6, 7)
+
+
+@pytest.mark.parametrize("variant,shape", [("skyeye_s", (1, 3, 32, 32)), ("skyeye_s", (3, 3, 64, 32)), ("skyeye_nano_l", (1, 3, 32, 64)),
+                                           ("skyeye_s", (1, 3, 96, 224))])
+def test_small_and_odd_inputs_run_and_match(variant, shape):
+    """Degenerate maps (P5 = 1x1 or 1x2 pixels, ragged tiles everywhere): the path must neither hang nor diverge."""
+    m, sd, cfg = _build(variant)
+    x = cases.image(shape)
+    det, raws = m(x.cuda())
+    torch.cuda.synchronize()
+    d_f32, r_f32 = om.forward(x, sd, cfg)
+    assert det.shape == d_f32.shape
+    for a, f in zip(raws, r_f32):
+        assert a.shape == f.shape and bool(torch.isfinite(a).all())
+        assert _rms(a, f) < 2 * RMS_BOUND[variant], _rms(a, f)
