@@ -1,0 +1,92 @@
+// Micro-benchmark: tcgen05.mma issue / execution rate per SM as a function of N (M = 128, K = 16 per instruction, bf16),
+// operand sources (A from shared memory or TMEM, B K-major or MN-major) and tcgen05.commit frequency.
+#include <cstdio>
+#include <cstdint>
+#include "common.cuh"
+using namespace skb;
+
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// mode 0: A smem (K-major), B K-major.  1: A TMEM, B K-major.  2: A TMEM, B MN-major.
+// nd = number of independent accumulators the instruction stream rotates over (1 = every MMA accumulates into the same D).
+__global__ void __launch_bounds__(128) k(int N, int mode, int commit_every, int reps, int tmem_cols, int nd, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = base, sB = base + 16384, bar = base + 16384 + 32768, bar2 = bar + 8, slot = bar + 16;
+    volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - smem_u32(smem_raw)));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0x3c003c00u;
+    if (warp == 0) {
+        if (lane == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); fence_barrier_init(); }
+        __syncwarp();
+        tmem_alloc(slot, (uint32_t)tmem_cols);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot_ptr;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = umma_idesc_bf16(128, N, 0, mode == 2 ? 1 : 0);
+        const uint32_t idesc_qk = umma_idesc_bf16(128, 64, 0, 0), idesc_pv = umma_idesc_bf16(128, 80, 0, 1);
+        const uint32_t tA = tmem + (uint32_t)(tmem_cols - 32);
+        const uint64_t ad = umma_desc(sA, 16, 1024, UMMA_SW128);
+        const uint64_t bdk = umma_desc(sB, 16, 1024, UMMA_SW128);
+        const uint64_t bdm = umma_desc(sB, 8192, 1024, UMMA_SW128);
+        long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const uint32_t d = tmem + (uint32_t)((kk % nd) * N);
+                if (mode == 0) umma_bf16_ss(d, ad + (uint64_t)(kk * 2), bdk + (uint64_t)(kk * 2), idesc, 1);
+                else if (mode == 1) umma_ts(d, tA + kk * 8, bdk + (uint64_t)(kk * 2), idesc, 1);
+                else if (mode == 2) umma_ts(d, tA + kk * 8, bdm + (uint64_t)(kk * 128), idesc, 1);
+                else {  // mode 3: the attention pattern -- a QK chain (N = 64, K-major B) interleaved with a PV chain (N = 80, MN-major B)
+                    umma_ts(tmem, tA + kk * 8, bdk + (uint64_t)(kk * 2), idesc_qk, 1);
+                    umma_ts(tmem + 128, tA + kk * 8, bdm + (uint64_t)(kk * 128), idesc_pv, 1);
+                }
+            }
+            if (commit_every == 1) umma_commit(bar2);
+            if (commit_every == 2) { umma_commit(bar2); umma_commit(bar2); }
+        }
+        umma_commit(bar);
+        long long t1 = clock64();
+        mbar_wait(bar, 0);
+        long long t2 = clock64();
+        out[blockIdx.x * 2] = t1 - t0;
+        out[blockIdx.x * 2 + 1] = t2 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)tmem_cols);
+}
+
+int main() {
+    long long* out;
+    cudaMalloc(&out, 296 * 16);
+    const int smem = 16384 + 32768 + 1024 + 64;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int reps = 2048;
+    const char* names[4] = {"A smem, B K-major ", "A TMEM, B K-major ", "A TMEM, B MN-major", "QK(64)+PV(80) pair"};
+    for (int ctas = 1; ctas <= 2; ++ctas)
+        for (int mode = 0; mode < 4; ++mode)
+            for (int N : {64, 128, 256})
+                for (int nd : {1, 2, 4}) {
+                    const int cols = ctas == 1 ? 512 : 256;
+                    if (nd * N > cols - 32) continue;
+                    if (mode == 3 && (N != 64 || nd != 1)) continue;
+                    k<<<148 * ctas, 128, smem>>>(N, mode, 0, reps, cols, nd, out);
+                    cudaError_t e = cudaDeviceSynchronize();
+                    long long h[2];
+                    cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
+                    const double per = mode == 3 ? 8.0 : 4.0;
+                    printf("%d CTA/SM %s N=%3d accumulators=%d: issue %.1f cyc/MMA, complete %.1f cyc/MMA per CTA (floor N/2 = %d)%s\n", ctas, names[mode], N,
+                           nd, (double)h[0] / (per * reps), (double)h[1] / (per * reps), N / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
+                }
+    return 0;
+}

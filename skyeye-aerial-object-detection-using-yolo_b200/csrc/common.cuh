@@ -85,23 +85,26 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 #ifndef SKB_MBAR_TIMEOUT_CYCLES
 #define SKB_MBAR_TIMEOUT_CYCLES 6000000000LL
 #endif
+// Measured (scripts/attn_prof.py, B200): mbarrier.try_wait with a suspend-time hint costs ~140 cycles even when the phase
+// has already completed; test_wait on a completed phase returns in ~30.  So: non-blocking test first, then the plain
+// (hint-less) try_wait loop.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    long long t0 = 0;
-    bool timing = false;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    const long long t0 = clock64();
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware instead of re-polling
-            : "memory");
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) break;
-        if (!timing) {
-            t0 = clock64();
-            timing = true;
-        } else if (clock64() - t0 > SKB_MBAR_TIMEOUT_CYCLES) {
+        if (clock64() - t0 > SKB_MBAR_TIMEOUT_CYCLES) {
             printf("skb: mbarrier timeout block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
             __trap();
         }

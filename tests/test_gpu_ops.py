@@ -137,9 +137,11 @@ def _attn_ref(qkv, heads):
     return o.transpose(1, 2).reshape(B, N, C)
 
 
-@pytest.mark.parametrize("b,h,w,heads", [(1, 16, 16, 1), (2, 16, 24, 2), (1, 4, 4, 4), (2, 10, 10, 1), (1, 40, 40, 4), (1, 64, 80, 2)])
+@pytest.mark.parametrize("b,h,w,heads", [(1, 16, 16, 1), (2, 16, 24, 2), (1, 4, 4, 4), (2, 10, 10, 1), (1, 40, 40, 4), (1, 64, 80, 2),
+                                           (1, 41, 100, 2), (1, 72, 72, 1)])
 def test_flash_attention_matches_oracle(b, h, w, heads):
-    """N = h*w tokens incl. ragged query and key tiles (16, 100, 384, 1600, 5120)."""
+    """N = h*w tokens incl. ragged query and key tiles (16, 100, 384, 1600, 5120); N >= 4096 runs two query tiles per CTA
+    (4100: the last CTA's second tile is entirely out of range; 5184 = 20.25 double tiles)."""
     from skyeye import engine as E
     C = heads * 64
     qkv = bf16r(randn(("att", b, h, w, heads), (b, h * w, 3 * C)))
