@@ -127,6 +127,10 @@ int skb_layernorm_bf16(const skb_view* x, const float* gamma, const float* beta,
  * style on tcgen05 (never materialises N x N).  qkv: bf16 view [B,H,W,3C] = in_proj output (q | k | v
  * on the channel axis); o: bf16 view [B,H,W,C]; head_dim must be 64. */
 int skb_flash_attn_bf16(const skb_view* qkv, const skb_view* o, int32_t heads, float scale, void* stream);
+/* Diagnostics only (no reference counterpart): with SKB_ATT_PROF=1 in the environment skb_flash_attn_bf16 runs an
+ * instrumented kernel that accumulates per-role phase cycle counts; this copies (and optionally clears) the 16 counters
+ * (layout: csrc/attention.cu, printed by scripts/attn_prof.py). */
+int skb_debug_attn_prof(unsigned long long* out16, int32_t reset);
 
 /* WindowedSelfAttention core (attention.py:372-395; the class is unwired in the reference):
  * per (window, head)  o = softmax(q * scale @ k^T + bias[head] (+ mask[window % n_mask])) @ v  for windows of

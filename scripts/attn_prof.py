@@ -24,15 +24,15 @@ def main():
     buf = (ctypes.c_ulonglong * 16)()
     E.flash_attn(qkv, o, heads, 0.125)
     torch.cuda.synchronize()
-    L.skb_debug_attn_prof(buf, 1)
+    L.skb_debug_attn_prof(ctypes.addressof(buf), 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     E.flash_attn(qkv, o, heads, 0.125)
     e1.record()
     torch.cuda.synchronize()
-    L.skb_debug_attn_prof(buf, 1)
+    L.skb_debug_attn_prof(ctypes.addressof(buf), 1)
     v = list(buf)
-    print(f"B={B} N={H * W} heads={heads}: {e0.elapsed_time(e1):.3f} ms  (instrumented) ONE={os.environ.get('SKB_ATT_ONE')} DBG={os.environ.get('SKB_ATT_DBG')}")
+    print(f"B={B} N={H * W} heads={heads}: {e0.elapsed_time(e1):.3f} ms  (instrumented variant, SKB_ATT_PROF=1)")
     its = {0: v[4], 1: v[4], 2: v[4], 3: v[4], 5: v[9], 6: v[9], 7: v[9], 8: v[9], 10: v[11], 12: v[9], 13: v[4]}
     for i, n in enumerate(NAMES):
         if i in its and its[i]:

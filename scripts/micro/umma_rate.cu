@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(128) k(int N, int mode, int commit_every, int 
         for (int r = 0; r < reps; ++r) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-                const uint32_t d = tmem + (uint32_t)((kk % nd) * N);
+                const uint32_t d = tmem + (uint32_t)((kk & (nd - 1)) * N);
                 if (mode == 0) umma_bf16_ss(d, ad + (uint64_t)(kk * 2), bdk + (uint64_t)(kk * 2), idesc, 1);
                 else if (mode == 1) umma_ts(d, tA + kk * 8, bdk + (uint64_t)(kk * 2), idesc, 1);
                 else if (mode == 2) umma_ts(d, tA + kk * 8, bdm + (uint64_t)(kk * 128), idesc, 1);
@@ -73,12 +73,13 @@ int main() {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const int reps = 2048;
     const char* names[4] = {"A smem, B K-major ", "A TMEM, B K-major ", "A TMEM, B MN-major", "QK(64)+PV(80) pair"};
-    for (int ctas = 1; ctas <= 2; ++ctas)
+    for (int ctas : {1, 2, 4})
         for (int mode = 0; mode < 4; ++mode)
             for (int N : {64, 128, 256})
                 for (int nd : {1, 2, 4}) {
-                    const int cols = ctas == 1 ? 512 : 256;
+                    const int cols = ctas == 1 ? 512 : ctas == 2 ? 256 : 128;
                     if (nd * N > cols - 32) continue;
+                    if (mode == 3 && ctas == 4) continue;
                     if (mode == 3 && (N != 64 || nd != 1)) continue;
                     k<<<148 * ctas, 128, smem>>>(N, mode, 0, reps, cols, nd, out);
                     cudaError_t e = cudaDeviceSynchronize();

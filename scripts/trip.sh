@@ -1,9 +1,11 @@
 mkdir -p gpurun_out
-L=gpurun_out/attn_prof2.log; : > $L
-SKB_ATT_NQ=1 SKB_ATT_PROF=1 timeout 300 python scripts/attn_prof.py >> $L 2>&1
-SKB_ATT_NQ=1 SKB_ATT_PROF=1 SKB_ATT_ONE=1 timeout 300 python scripts/attn_prof.py >> $L 2>&1
-SKB_ATT_NQ=1 SKB_ATT_PROF=1 SKB_ATT_ONE=1 SKB_ATT_DBG=2 timeout 300 python scripts/attn_prof.py >> $L 2>&1
-SKB_ATT_NQ=1 SKB_ATT_PROF=1 SKB_ATT_DBG=2 timeout 300 python scripts/attn_prof.py >> $L 2>&1
-SKB_ATT_NQ=1 SKB_ATT_PROF=1 SKB_ATT_DBG=1 timeout 300 python scripts/attn_prof.py >> $L 2>&1
-SKB_ATT_NQ=2 SKB_ATT_PROF=1 timeout 300 python scripts/attn_prof.py >> $L 2>&1
+L=gpurun_out/attn_v4.log; : > $L
+SKB_ATT_V2=1 timeout 900 python -m pytest tests/test_gpu_ops.py -m gpu -q -k "flash" 2>&1 | tail -3 >> $L
+run() { echo "== $*" >> $L; env "$@" timeout 300 python scripts/bench_layers.py --only attn_p3,attn_p4,attn_p5 --iters 7 2>&1 | grep attn_ >> $L; }
+run SKB_ATT_V2=0
+run SKB_ATT_V2=1
+run SKB_ATT_V2=1 SKB_ATT_POLY=0
+run SKB_ATT_V2=1 SKB_ATT_POLY=16
+run SKB_ATT_V2=0
 cat $L
+python scripts/bench_nms_stress.py > gpurun_out/nms_stress.json 2> gpurun_out/nms_stress.err; cat gpurun_out/nms_stress.json; tail -3 gpurun_out/nms_stress.err

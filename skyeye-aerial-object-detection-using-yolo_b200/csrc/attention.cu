@@ -30,10 +30,17 @@ constexpr int ATT_BQ = 128, ATT_BKV = 64, ATT_D = 64, ATT_KVS = 4;
 constexpr int ATT_Q_BYTES = ATT_BQ * ATT_D * 2;     // 16 KB
 constexpr int ATT_KV_BYTES = ATT_BKV * ATT_D * 2;   // 8 KB
 constexpr int ATT_ONES_BYTES = ATT_BKV * 128;       // 8 KB of bf16 1.0: extra B columns that make the PV MMA emit the row sums
-constexpr int ATT_SMEM = ATT_Q_BYTES + 2 * ATT_KVS * ATT_KV_BYTES + ATT_ONES_BYTES + 1024 + 256;
+constexpr int ATT_SMEM = ATT_Q_BYTES + 2 * ATT_KVS * ATT_KV_BYTES + ATT_ONES_BYTES + 1024 + 256;  // + barriers, TMEM slot, PROF stamps
 constexpr int ATT_ON = ATT_D + 16;                  // PV accumulator width: 64 output dims + 16 copies of sum_k P
 constexpr uint32_t ATT_TMEM_COLS = 256;             // S0/P0 [0,64) S1/P1 [64,128) O [128,208) Q [208,240)
 constexpr int ATT_POLY_DEFAULT = 8;                 // exponentials per 64 evaluated on the FMA pipes (0, 8, 16, 24, 32)
+
+// Diagnostics (SKB_ATT_PROF=1 runs the instrumented variant; scripts/attn_prof.py prints the table): cycle sums per role
+// phase, accumulated with atomics by lane 0 of each role warp.
+//  0 softmax: wait S   1 softmax: TMEM load   2 softmax: exponentials / max / pack   3 softmax: TMEM store + arrive
+//  4 softmax iterations   5 MMA: wait P   6 MMA: issue PV   7 MMA: wait K/V   8 MMA: issue QK   9 MMA iterations
+// 10 TMA: wait empty stage   11 TMA iterations   12 hop P-arrive -> MMA warp awake   13 hop S-commit -> softmax awake
+__device__ unsigned long long g_att_prof[16];
 
 struct AttnParams {
     int N, heads, C, T;
@@ -75,7 +82,7 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
     return r;
 }
 
-template <int ATT_POLY>
+template <int ATT_POLY, bool PROF = false>
 __global__ void __launch_bounds__(192, 2)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -95,6 +102,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t o_done = bar0 + 8u * (6 + 2 * ATT_KVS);
     const uint32_t slot = bar0 + 8u * (7 + 2 * ATT_KVS);
     volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - raw));
+    volatile long long* stamp = reinterpret_cast<volatile long long*>(smem_raw + (slot + 16 - raw));  // PROF: [sb] P arrive, [2 + sb] S commit
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
@@ -129,31 +137,45 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if (lane == 0) {
             mbar_expect_tx(q_full, ATT_Q_BYTES);
             tma_load_3d(sQ, &tmQ, q_full, head * ATT_D, qt * ATT_BQ, b);
+            long long pf_tma = 0;
             for (int j = 0; j < T; ++j) {
                 const int s = j % ATT_KVS;
                 const uint32_t u = (uint32_t)(j / ATT_KVS);
+                long long c0 = 0;
+                if (PROF) c0 = clock64();
                 mbar_wait(kv_empty(s), (u & 1u) ^ 1u);
+                if (PROF) pf_tma += clock64() - c0;
                 mbar_expect_tx(kv_full(s), 2 * ATT_KV_BYTES);
                 tma_load_3d(sK0 + s * ATT_KV_BYTES, &tmKV, kv_full(s), p.C + head * ATT_D, j * ATT_BKV, b);
                 tma_load_3d(sV0 + s * ATT_KV_BYTES, &tmKV, kv_full(s), 2 * p.C + head * ATT_D, j * ATT_BKV, b);
+            }
+            if (PROF) {
+                atomicAdd(&g_att_prof[10], (unsigned long long)pf_tma);
+                atomicAdd(&g_att_prof[11], (unsigned long long)T);
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BQ, ATT_BKV, 0, 0);  // A = Q (TMEM), B = K (K-major)
         constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BQ, ATT_ON, 0, 1);   // A = P (TMEM), B = [V | ones] (MN-major)
+        long long pf_m[4] = {0, 0, 0, 0}, pf_hop = 0;
         auto issue_qk = [&](int j) {
             const int s = j % ATT_KVS, sb = j & 1;
+            long long c0 = 0, c1 = 0;
+            if (PROF) c0 = clock64();
             mbar_wait(kv_full(s), (uint32_t)(j / ATT_KVS) & 1u);
+            if (PROF) c1 = clock64();
             tc_fence_after();
             if (lane == 0) {
                 const uint64_t bd = umma_desc(sK0 + s * ATT_KV_BYTES, 16, 1024, UMMA_SW128);
 #pragma unroll
                 for (int k = 0; k < ATT_D / 16; ++k)  // 16 bf16 of A = 8 TMEM columns
                     umma_bf16_ts(tmem + sb * ATT_BKV, tmem_Q + k * 8, bd + (uint64_t)(k * 2), idesc_qk, k > 0);
+                if (PROF) stamp[2 + sb] = clock64();
                 umma_commit(s_full(sb));
             }
             __syncwarp();
+            if (PROF) { pf_m[2] += c1 - c0; pf_m[3] += clock64() - c1; }
         };
         mbar_wait(q_ready, 0);
         tc_fence_after();
@@ -161,7 +183,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if (T > 1) issue_qk(1);
         for (int j = 0; j < T; ++j) {
             const int s = j % ATT_KVS, sb = j & 1;
+            long long c0 = 0, c1 = 0;
+            if (PROF) c0 = clock64();
             mbar_wait(p_full(sb), (uint32_t)(j >> 1) & 1u);
+            if (PROF) { c1 = clock64(); pf_hop += c1 - stamp[sb]; }
             tc_fence_after();
             if (lane == 0) {
                 // V tile [64 keys][64 d]: MN-major, 128-byte rows, 8-row groups 1024 B apart, 16 keys per MMA = 2048 B.
@@ -177,7 +202,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 umma_commit(o_done);
             }
             __syncwarp();
+            if (PROF) { pf_m[0] += c1 - c0; pf_m[1] += clock64() - c1; }
             if (j + 2 < T) issue_qk(j + 2);  // reuses S/P buffer sb: ordered behind PV(j) by in-order MMA execution
+        }
+        if (PROF && lane == 0) {
+            for (int i = 0; i < 4; ++i) atomicAdd(&g_att_prof[5 + i], (unsigned long long)pf_m[i]);
+            atomicAdd(&g_att_prof[9], (unsigned long long)T);
+            atomicAdd(&g_att_prof[12], (unsigned long long)pf_hop);
         }
     } else {
         // ===================== softmax + epilogue: thread <-> query row =====================
@@ -206,9 +237,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         float m_ref = -INFINITY;
         const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+        long long pf_s[4] = {0, 0, 0, 0}, pf_hop = 0;
         for (int j = 0; j < T; ++j) {
             const int sb = j & 1;
+            long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            if (PROF) c0 = clock64();
             mbar_wait(s_full(sb), (uint32_t)(j >> 1) & 1u);
+            if (PROF) { c1 = clock64(); pf_hop += c1 - stamp[2 + sb]; }
             tc_fence_after();
             uint32_t sv[64];
             {
@@ -218,6 +253,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 tmem_ld32(tmem + lane_addr + sb * ATT_BKV + 32, hi);
             }
             tmem_ld_wait();
+            if (PROF) c2 = clock64();
             // row max of the raw scores (keys beyond N masked on the ragged last tile)
             const int kbase = j * ATT_BKV;
             if (kbase + ATT_BKV > p.N) {
@@ -284,11 +320,19 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 compute_p(m_ref);
             }
             // P (bf16, K-major: lane = query row, column c holds keys 2c, 2c+1) over the first half of S
+            if (PROF) c3 = clock64();
             tmem_st32(tmem + lane_addr + sb * ATT_BKV, pk);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
+            if (PROF && lane == 0) stamp[sb] = clock64();  // last writer = (approximately) the last arriving warp
             if (lane == 0) mbar_arrive(p_full(sb));
+            if (PROF) { pf_s[0] += c1 - c0; pf_s[1] += c2 - c1; pf_s[2] += c3 - c2; pf_s[3] += clock64() - c3; }
+        }
+        if (PROF && lane == 0) {
+            for (int i = 0; i < 4; ++i) atomicAdd(&g_att_prof[i], (unsigned long long)pf_s[i]);
+            atomicAdd(&g_att_prof[4], (unsigned long long)T);
+            atomicAdd(&g_att_prof[13], (unsigned long long)pf_hop);
         }
         // ---- epilogue: O / l -> bf16 ----
         mbar_wait(o_done, (uint32_t)(T - 1) & 1u);
@@ -349,7 +393,7 @@ extern "C" int skb_flash_attn_bf16(const skb_view* qkv, const skb_view* o, int32
     p.N = N; p.heads = heads; p.C = C; p.T = (N + ATT_BKV - 1) / ATT_BKV;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.out = (__nv_bfloat16*)o->ptr; p.out_pitch = o->pitch;
-    static int poly = -1;
+    static int poly = -1, prof = 0;
     if (poly < 0) {  // tuning knob (not part of the ABI): SKB_ATT_POLY in {0, 8, 16, 24, 32}
         const char* e = getenv("SKB_ATT_POLY");
         poly = e ? atoi(e) : ATT_POLY_DEFAULT;
@@ -359,9 +403,17 @@ extern "C" int skb_flash_attn_bf16(const skb_view* qkv, const skb_view* o, int32
         SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        e = getenv("SKB_ATT_PROF");  // diagnostics: instrumented variant (skb_debug_attn_prof reads the counters)
+        prof = e ? atoi(e) : 0;
     }
     dim3 grid((N + ATT_BQ - 1) / ATT_BQ, heads, B);
     cudaStream_t st = (cudaStream_t)stream;
+    if (prof) {
+        flash_attn_kernel<8, true><<<grid, 192, ATT_SMEM, st>>>(tmQ, tmKV, p);
+        SKB_LAUNCH_CHECK();
+        return SKB_OK;
+    }
     switch (poly) {
         case 0: flash_attn_kernel<0><<<grid, 192, ATT_SMEM, st>>>(tmQ, tmKV, p); break;
         case 8: flash_attn_kernel<8><<<grid, 192, ATT_SMEM, st>>>(tmQ, tmKV, p); break;
@@ -370,6 +422,16 @@ extern "C" int skb_flash_attn_bf16(const skb_view* qkv, const skb_view* o, int32
         default: flash_attn_kernel<16><<<grid, 192, ATT_SMEM, st>>>(tmQ, tmKV, p); break;
     }
     SKB_LAUNCH_CHECK();
+    return SKB_OK;
+}
+
+// Diagnostics: copies (and optionally clears) the 16 phase counters of the SKB_ATT_PROF=1 kernel variant.
+extern "C" int skb_debug_attn_prof(unsigned long long* out16, int32_t reset) {
+    if (out16) SKB_CUDA(cudaMemcpyFromSymbol(out16, g_att_prof, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        SKB_CUDA(cudaMemcpyToSymbol(g_att_prof, z, sizeof(z)));
+    }
     return SKB_OK;
 }
 

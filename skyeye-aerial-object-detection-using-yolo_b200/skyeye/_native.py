@@ -99,6 +99,7 @@ _SIGNATURES = {
                                     c_int32, c_float, c_float, c_void_p, c_size_t, c_void_p]),
     "skb_layernorm_bf16": (c_int32, [POINTER(skb_view), c_void_p, c_void_p, c_float, POINTER(skb_view), c_void_p]),
     "skb_flash_attn_bf16": (c_int32, [POINTER(skb_view), POINTER(skb_view), c_int32, c_float, c_void_p]),
+    "skb_debug_attn_prof": (c_int32, [c_void_p, c_int32]),
     "skb_window_attn_bf16": (c_int32, [POINTER(skb_view), c_void_p, c_void_p, c_int32, POINTER(skb_view), c_int32, c_float, c_void_p]),
     "skb_decode_f32": (c_int32, [POINTER(skb_view), c_int32, c_int32, c_int32, POINTER(c_float), c_int32, c_int32,
                                  c_void_p, POINTER(c_void_p), c_void_p]),
