@@ -1,11 +1,5 @@
 mkdir -p gpurun_out
-L=gpurun_out/attn_v4.log; : > $L
-SKB_ATT_V2=1 timeout 900 python -m pytest tests/test_gpu_ops.py -m gpu -q -k "flash" 2>&1 | tail -3 >> $L
-run() { echo "== $*" >> $L; env "$@" timeout 300 python scripts/bench_layers.py --only attn_p3,attn_p4,attn_p5 --iters 7 2>&1 | grep attn_ >> $L; }
-run SKB_ATT_V2=0
-run SKB_ATT_V2=1
-run SKB_ATT_V2=1 SKB_ATT_POLY=0
-run SKB_ATT_V2=1 SKB_ATT_POLY=16
-run SKB_ATT_V2=0
-cat $L
-python scripts/bench_nms_stress.py > gpurun_out/nms_stress.json 2> gpurun_out/nms_stress.err; cat gpurun_out/nms_stress.json; tail -3 gpurun_out/nms_stress.err
+bash scripts/gpu_tests.sh t31 conv model
+timeout 600 python scripts/bench_layers.py --iters 7 --only c3x3_128_160,c3x3_256_80,c3x3_64_320,c3x3_512_40,c1x1_128_128_160 2>&1 | tee gpurun_out/layers_2issuers.log
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r1n.log 2> gpurun_out/bench_r1n.err
+tail -1 gpurun_out/bench_r1n.log | cut -c1-200

@@ -479,8 +479,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 //   * every weight tile (BN x 64, one per tap and chunk) is used by both accumulators.
 // Bytes into the SM per 256 pixels: 54 KB*chunks + 9*chunks*BN*128 B, vs 2*9*chunks*(16 KB + BN*128 B) before
 // (128->128: 396 KB vs 1152 KB), which makes these layers tensor-bound.
-// Warp roles: 0 = halo TMA producer, 10 = weight TMA producer, 1 = MMA issuer, 2..5 / 6..9 = epilogue of the
-// left / right accumulator.  TMEM: 2 tiles in flight x 2 halves x BN columns.
+// Warp roles: 0 = halo TMA producer, 10 = weight TMA producer, 1 / 11 = MMA issuers of the left / right accumulator,
+// 2..5 / 6..9 = epilogue of the left / right accumulator.  TMEM: 2 tiles in flight x 2 halves x BN columns.
 // =============================================================================================
 struct HaloParams {
     int tiles_w, tiles_h;
@@ -517,7 +517,7 @@ __device__ __forceinline__ void halo_decode(const HaloParams& p, int item, int& 
 }
 
 template <int BN>
-__global__ void __launch_bounds__(352, 1)
+__global__ void __launch_bounds__(384, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const HaloParams p) {
     using Cfg = HaloCfg<BN>;
@@ -535,10 +535,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     auto h_empty = [&](int s) { return bar0 + 8u * (HS + s); };
     auto b_full = [&](int s) { return bar0 + 8u * (2 * HS + s); };
     auto b_empty = [&](int s) { return bar0 + 8u * (2 * HS + BS + s); };
-    auto tfull = [&](int s) { return bar0 + 8u * (2 * HS + 2 * BS + s); };
-    auto tempty = [&](int s) { return bar0 + 8u * (2 * HS + 2 * BS + 2 + s); };
-    auto res_full = [&](int s) { return bar0 + 8u * (2 * HS + 2 * BS + 4 + s); };
-    const uint32_t slot = bar0 + 8u * (2 * HS + 2 * BS + 4 + 2 * NB);
+    auto tfull = [&](int buf, int half) { return bar0 + 8u * (2 * HS + 2 * BS + buf * 2 + half); };       // per accumulator half
+    auto tempty = [&](int buf, int half) { return bar0 + 8u * (2 * HS + 2 * BS + 4 + buf * 2 + half); };
+    auto res_full = [&](int s) { return bar0 + 8u * (2 * HS + 2 * BS + 8 + s); };
+    const uint32_t slot = bar0 + 8u * (2 * HS + 2 * BS + 8 + 2 * NB);
     volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -551,9 +551,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < HS; ++s) { mbar_init(h_full(s), 1); mbar_init(h_empty(s), 1); }
-            for (int s = 0; s < BS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-            for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 8); }
+            for (int s = 0; s < HS; ++s) { mbar_init(h_full(s), 1); mbar_init(h_empty(s), 2); }  // released by both MMA issuers
+            for (int s = 0; s < BS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 2); }
+            for (int s = 0; s < 4; ++s) { mbar_init(tfull(s >> 1, s & 1), 1); mbar_init(tempty(s >> 1, s & 1), 4); }
             for (int s = 0; s < 2 * NB; ++s) mbar_init(res_full(s), 1);
             fence_barrier_init();
         }
@@ -600,15 +600,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 || warp == 11) {
+        // ===================== MMA issuers: warp 1 = left half accumulator, warp 11 = right half =====================
+        // One thread issues a tcgen05.mma at most every ~80 cycles whatever its N (scripts/micro/umma_rate.cu), i.e. 8 MMAs
+        // per tap cost one issuer ~680 cycles against 4*BN cycles of tensor time: with BN <= 128 a single issuer was the
+        // bound.  Each half has its own issuer, accumulator and full/empty barriers; stages are released by both.
+        const int half = warp == 11 ? 1 : 0;
         constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
         int hs = 0, bs = 0, buf = 0;
         uint32_t hph = 0, bph = 0, tph = 0;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-            mbar_wait(tempty(buf), tph ^ 1);
+            mbar_wait(tempty(buf, half), tph ^ 1);
             tc_fence_after();
-            const uint32_t d0 = tmem_base + (uint32_t)((buf * 2) * BN), d1 = d0 + (uint32_t)BN;
+            const uint32_t d0 = tmem_base + (uint32_t)((buf * 2 + half) * BN);
             for (int c = 0; c < p.cchunks; ++c) {
                 mbar_wait(h_full(hs), hph);
                 const uint32_t hbase = sH0 + hs * Cfg::HALO_BYTES;
@@ -617,21 +621,18 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     tc_fence_after();
                     if (lane == 0) {
                         const int dy = t / 3, dx = t - dy * 3;
-                        const uint32_t a0 = hbase + (uint32_t)(dy * 3072 + dx * 128);
+                        const uint32_t a0 = hbase + (uint32_t)(dy * 3072 + dx * 128 + half * 1024);  // right half: 8 pixels further
                         // start not 1024-aligned when dx != 0: the 128B-swizzle XOR is taken from the absolute smem
                         // address bits [7,10) (measured: correct with the descriptor's base-offset field left 0)
                         const uint64_t ad0 = umma_desc(a0, 16, 3072, UMMA_SW128);
-                        const uint64_t ad1 = umma_desc(a0 + 1024, 16, 3072, UMMA_SW128);  // right half: 8 pixels further
                         const uint64_t bd = umma_desc(sB0 + bs * Cfg::B_BYTES, 16, 1024, UMMA_SW128);
                         const uint32_t acc = (c > 0 || t > 0) ? 1u : 0u;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) umma_bf16_ss(d0, ad0 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (acc || k > 0) ? 1u : 0u);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_bf16_ss(d1, ad1 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (acc || k > 0) ? 1u : 0u);
                         umma_commit(b_empty(bs));
                         if (t == 8) {
                             umma_commit(h_empty(hs));
-                            if (c == p.cchunks - 1) umma_commit(tfull(buf));
+                            if (c == p.cchunks - 1) umma_commit(tfull(buf, half));
                         }
                     }
                     __syncwarp();
@@ -681,7 +682,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 named_bar_sync(barid, GT);
             }
             const uint32_t acc = tmem_base + lane_addr + (uint32_t)((buf * 2 + g) * BN);
-            mbar_wait(tfull(buf), tph);
+            mbar_wait(tfull(buf, g), tph);
             tc_fence_after();
 #pragma unroll 1
             for (int sub = 0; sub < NSUB; ++sub, ++qseq) {
@@ -701,7 +702,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (last) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty(buf));
+                        if (lane == 0) mbar_arrive(tempty(buf, g));
                     }
                     epi_piece_bf16(v, sbias_g + 4u * (uint32_t)c0, p.act, p.has_res != 0, rowp, 0u, sw);
                     epi_piece_bf16(v + 32, sbias_g + 4u * (uint32_t)(c0 + 32), p.act, p.has_res != 0, rowp, 4u, sw);
@@ -755,7 +756,7 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(352);
+    cfg.blockDim = dim3(384);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
