@@ -1,15 +1,17 @@
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_r1p.log 2>&1; tail -2 gpurun_out/smoke_r1p.log
-bash scripts/gpu_tests.sh t33 conv ops nms model
-python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/bench_ref_r1p.log 2> gpurun_out/bench_ref_r1p.err; tail -1 gpurun_out/bench_ref_r1p.log | cut -c1-300
-python bench.py --steps 10 --warmup 3 --profile-json gpurun_out/bench_profile_r1p.json > gpurun_out/bench_r1p.log 2> gpurun_out/bench_r1p.err
-tail -1 gpurun_out/bench_r1p.log | cut -c1-250
-SKB_ATT_PROF=1 python scripts/attn_prof.py > gpurun_out/attn_prof_r1p.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_r1p.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-latency --no-graph > gpurun_out/ncu_r1p.log 2>&1
-echo "launch list rc $?"
-ncu --set full --clock-control none --import-source on -k regex:flash_attn -s 9 -c 3 -o gpurun_out/prof_r1p_attn -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-latency --no-graph > gpurun_out/ncu_r1p_attn.log 2>&1
-echo "attn capture rc $?"
-ncu --set full --clock-control none --import-source on -k regex:conv3x3_halo -c 3 -o gpurun_out/prof_r1p_halo -f python scripts/bench_layers.py --once --only c3x3_128_160,c3x3_256_80,c3x3_64_320 > gpurun_out/ncu_r1p_halo.log 2>&1
-echo "halo capture rc $?"
-ls -la gpurun_out/*.ncu-rep | tail -3
+bash scripts/gpu_tests.sh t34 conv ops model
+run() { tag=$1; shift; env "$@" python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-latency > gpurun_out/bench_ab_$tag.log 2> gpurun_out/bench_ab_$tag.err; python - <<PY
+import json
+l=[x for x in open('gpurun_out/bench_ab_$tag.log') if x.startswith('{')]
+if l:
+    d=json.loads(l[-1]); print('$tag', round(d['value'],1), round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value'],1), d['clocks']['sm_mhz'], d['clocks']['power_w_max'], 'attn', d['kernels']['attention']['ms_per_step'], 'conv', d['kernels']['conv']['ms_per_step'])
+else:
+    print('$tag', 'no line'); print(open('gpurun_out/bench_ab_$tag.err').read()[-800:])
+PY
+}
+run new1 A=1
+run old1 SKB_CONV_PAIR=0 SKB_ATT_NQ=1
+run nq2only SKB_CONV_PAIR=0
+run paironly SKB_ATT_NQ=1
+run new2 A=1
+run old2 SKB_CONV_PAIR=0 SKB_ATT_NQ=1

@@ -17,8 +17,13 @@
 // S/P buffer of tile j right after PV(j) has been issued.
 // The in_proj output [B, N, 3C] is read in place: one 3-D tensor map {channel, token, image} serves
 // Q, K and V (different channel coordinates), ragged N is TMA zero fill + a -inf mask on the last tile.
-// 2 CTAs are resident per SM (89 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the
-// other's MMAs.  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = softmax/epilogue.
+// NQ = 1 (short sequences): 2 CTAs are resident per SM (89 KB smem, 256 TMEM columns each) so one CTA's softmax
+// overlaps the other's MMAs; warp roles 0 = TMA producer, 1 = MMA issuer, 2..5 = softmax/epilogue.
+// NQ = 2 (N >= 4096): ONE CTA per SM owns two query tiles that share the K/V stream; each tile has its own MMA-issuing
+// warp (1, 2), softmax warpgroup (4..7, 8..11) and 256 TMEM columns, and the two run unsynchronised.  Kernel time alone
+// is the same as two NQ = 1 CTAs (profiles/r1m_attention_pipeline.md), but the K/V traffic L2 -> shared memory and the
+// TMA writes are halved, and under the board's 1000 W power cap (which holds the SM clock near 1.7 GHz for the whole
+// step) that buys clock: +1.6 % images/s on the full step, measured on the same box.
 #include <math.h>
 #include <stdlib.h>
 
@@ -26,17 +31,28 @@
 
 namespace skb {
 
-constexpr int ATT_BQ = 128, ATT_BKV = 64, ATT_D = 64, ATT_KVS = 4;
+constexpr int ATT_BQ = 128, ATT_BKV = 64, ATT_D = 64;
 constexpr int ATT_Q_BYTES = ATT_BQ * ATT_D * 2;     // 16 KB
 constexpr int ATT_KV_BYTES = ATT_BKV * ATT_D * 2;   // 8 KB
 constexpr int ATT_ONES_BYTES = ATT_BKV * 128;       // 8 KB of bf16 1.0: extra B columns that make the PV MMA emit the row sums
-constexpr int ATT_SMEM = ATT_Q_BYTES + 2 * ATT_KVS * ATT_KV_BYTES + ATT_ONES_BYTES + 1024 + 256;  // + barriers, TMEM slot, PROF stamps
 constexpr int ATT_ON = ATT_D + 16;                  // PV accumulator width: 64 output dims + 16 copies of sum_k P
-constexpr uint32_t ATT_TMEM_COLS = 256;             // S0/P0 [0,64) S1/P1 [64,128) O [128,208) Q [208,240)
 constexpr int ATT_POLY_DEFAULT = 8;                 // exponentials per 64 evaluated on the FMA pipes (0, 8, 16, 24, 32)
 
-// Diagnostics (SKB_ATT_PROF=1 runs the instrumented variant; scripts/attn_prof.py prints the table): cycle sums per role
-// phase, accumulated with atomics by lane 0 of each role warp.
+// NQ = query tiles (of 128 rows) per CTA.  NQ = 1: 192 threads, 2 CTAs per SM.  NQ = 2: ONE CTA per SM whose two
+// query tiles share the K/V stream in shared memory -- the K/V traffic from L2 (which alone takes half of the NQ = 1
+// kernel's time at N = 25600: 12.7 TB/s, the L2 limit) and the TMA writes into shared memory are halved.  Each query
+// tile has its own MMA-issuing warp, softmax warpgroup and 256 TMEM columns; the two run unsynchronised.
+template <int NQ>
+struct AttCfg {
+    static constexpr int KVS = NQ == 1 ? 4 : 8;          // K/V ring stages (16 KB each)
+    static constexpr int THREADS = NQ == 1 ? 192 : 384;  // warp 0 TMA, warps 1..NQ MMA, 4 softmax warps per query tile
+    static constexpr int SW0 = NQ == 1 ? 2 : 4;          // first softmax warp
+    static constexpr int CTAS_PER_SM = NQ == 1 ? 2 : 1;
+    static constexpr int SMEM = NQ * ATT_Q_BYTES + 2 * KVS * ATT_KV_BYTES + ATT_ONES_BYTES + 1024 + 512;  // barriers, TMEM slot, PROF stamps
+    static constexpr uint32_t TMEM_COLS = 256 * NQ;      // per query tile: S0/P0 [0,64) S1/P1 [64,128) O [128,208) Q [208,240)
+};
+
+// Diagnostics (SKB_ATT_PROF=1): cycle sums per role phase, accumulated with atomics by lane 0 of each role warp.
 //  0 softmax: wait S   1 softmax: TMEM load   2 softmax: exponentials / max / pack   3 softmax: TMEM store + arrive
 //  4 softmax iterations   5 MMA: wait P   6 MMA: issue PV   7 MMA: wait K/V   8 MMA: issue QK   9 MMA iterations
 // 10 TMA: wait empty stage   11 TMA iterations   12 hop P-arrive -> MMA warp awake   13 hop S-commit -> softmax awake
@@ -82,30 +98,31 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
     return r;
 }
 
-template <int ATT_POLY, bool PROF = false>
-__global__ void __launch_bounds__(192, 2)
+template <int ATT_POLY, int NQ, bool PROF = false>
+__global__ void __launch_bounds__(AttCfg<NQ>::THREADS, AttCfg<NQ>::CTAS_PER_SM)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
+    using Cfg = AttCfg<NQ>;
+    constexpr int KVS = Cfg::KVS;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     const uint32_t sQ = base;
-    const uint32_t sK0 = sQ + ATT_Q_BYTES;
-    const uint32_t sV0 = sK0 + ATT_KVS * ATT_KV_BYTES;
-    const uint32_t sOnes = sV0 + ATT_KVS * ATT_KV_BYTES;
+    const uint32_t sK0 = sQ + NQ * ATT_Q_BYTES;
+    const uint32_t sV0 = sK0 + KVS * ATT_KV_BYTES;
+    const uint32_t sOnes = sV0 + KVS * ATT_KV_BYTES;
     const uint32_t bar0 = sOnes + ATT_ONES_BYTES;
-    const uint32_t q_full = bar0;
-    const uint32_t q_ready = bar0 + 8u;
-    auto kv_full = [&](int s) { return bar0 + 8u * (2 + s); };
-    auto kv_empty = [&](int s) { return bar0 + 8u * (2 + ATT_KVS + s); };
-    auto s_full = [&](int s) { return bar0 + 8u * (2 + 2 * ATT_KVS + s); };
-    auto p_full = [&](int s) { return bar0 + 8u * (4 + 2 * ATT_KVS + s); };
-    const uint32_t o_done = bar0 + 8u * (6 + 2 * ATT_KVS);
-    const uint32_t slot = bar0 + 8u * (7 + 2 * ATT_KVS);
+    auto q_full = [&](int g) { return bar0 + 8u * g; };
+    auto q_ready = [&](int g) { return bar0 + 8u * (NQ + g); };
+    auto kv_full = [&](int s) { return bar0 + 8u * (2 * NQ + s); };
+    auto kv_empty = [&](int s) { return bar0 + 8u * (2 * NQ + KVS + s); };
+    auto s_full = [&](int g, int s) { return bar0 + 8u * (2 * NQ + 2 * KVS + 2 * g + s); };
+    auto p_full = [&](int g, int s) { return bar0 + 8u * (4 * NQ + 2 * KVS + 2 * g + s); };
+    auto o_done = [&](int g) { return bar0 + 8u * (6 * NQ + 2 * KVS + g); };
+    const uint32_t slot = bar0 + 8u * (7 * NQ + 2 * KVS);
     volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - raw));
-    volatile long long* stamp = reinterpret_cast<volatile long long*>(smem_raw + (slot + 16 - raw));  // PROF: [sb] P arrive, [2 + sb] S commit
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    const int qt0 = blockIdx.x * NQ, head = blockIdx.y, b = blockIdx.z;
     const int T = p.T;
 
     if (warp == 0 && lane == 0) {
@@ -114,33 +131,34 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     if (warp == 1) {
         if (lane == 0) {
-            mbar_init(q_full, 1);
-            mbar_init(q_ready, 4);
-            for (int s = 0; s < ATT_KVS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-            for (int s = 0; s < 2; ++s) { mbar_init(s_full(s), 1); mbar_init(p_full(s), 4); }
-            mbar_init(o_done, 1);
+            for (int g = 0; g < NQ; ++g) {
+                mbar_init(q_full(g), 1);
+                mbar_init(q_ready(g), 4);
+                mbar_init(o_done(g), 1);
+                for (int s = 0; s < 2; ++s) { mbar_init(s_full(g, s), 1); mbar_init(p_full(g, s), 4); }
+            }
+            for (int s = 0; s < KVS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), NQ); }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc(slot, ATT_TMEM_COLS);
+        tmem_alloc(slot, Cfg::TMEM_COLS);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *slot_ptr;
-    const uint32_t tmem_O = tmem + 128;
-    const uint32_t tmem_L = tmem_O + ATT_D;  // row sums (first of 16 identical columns)
-    const uint32_t tmem_Q = tmem + 208;
+    const uint32_t tmem_base = *slot_ptr;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_expect_tx(q_full, ATT_Q_BYTES);
-            tma_load_3d(sQ, &tmQ, q_full, head * ATT_D, qt * ATT_BQ, b);
+            for (int g = 0; g < NQ; ++g) {
+                mbar_expect_tx(q_full(g), ATT_Q_BYTES);
+                tma_load_3d(sQ + g * ATT_Q_BYTES, &tmQ, q_full(g), head * ATT_D, (qt0 + g) * ATT_BQ, b);
+            }
             long long pf_tma = 0;
             for (int j = 0; j < T; ++j) {
-                const int s = j % ATT_KVS;
-                const uint32_t u = (uint32_t)(j / ATT_KVS);
+                const int s = j % KVS;
+                const uint32_t u = (uint32_t)(j / KVS);
                 long long c0 = 0;
                 if (PROF) c0 = clock64();
                 mbar_wait(kv_empty(s), (u & 1u) ^ 1u);
@@ -154,16 +172,21 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 atomicAdd(&g_att_prof[11], (unsigned long long)T);
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp <= NQ) {
+        // ===================== MMA issuer of query tile g =====================
+        const int g = warp - 1;
+        const uint32_t tmem = tmem_base + g * 256;
+        const uint32_t tmem_O = tmem + 128;
+        const uint32_t tmem_Q = tmem + 208;
         constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BQ, ATT_BKV, 0, 0);  // A = Q (TMEM), B = K (K-major)
         constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BQ, ATT_ON, 0, 1);   // A = P (TMEM), B = [V | ones] (MN-major)
         long long pf_m[4] = {0, 0, 0, 0}, pf_hop = 0;
+        volatile long long* stamp = reinterpret_cast<volatile long long*>(smem_raw + (slot + 16 - raw));  // [g][sb]: P arrive, [2NQ + ..]: S commit
         auto issue_qk = [&](int j) {
-            const int s = j % ATT_KVS, sb = j & 1;
+            const int s = j % KVS, sb = j & 1;
             long long c0 = 0, c1 = 0;
             if (PROF) c0 = clock64();
-            mbar_wait(kv_full(s), (uint32_t)(j / ATT_KVS) & 1u);
+            mbar_wait(kv_full(s), (uint32_t)(j / KVS) & 1u);
             if (PROF) c1 = clock64();
             tc_fence_after();
             if (lane == 0) {
@@ -171,22 +194,22 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
                 for (int k = 0; k < ATT_D / 16; ++k)  // 16 bf16 of A = 8 TMEM columns
                     umma_bf16_ts(tmem + sb * ATT_BKV, tmem_Q + k * 8, bd + (uint64_t)(k * 2), idesc_qk, k > 0);
-                if (PROF) stamp[2 + sb] = clock64();
-                umma_commit(s_full(sb));
+                if (PROF) stamp[2 * NQ + 2 * g + sb] = clock64();
+                umma_commit(s_full(g, sb));
             }
             __syncwarp();
             if (PROF) { pf_m[2] += c1 - c0; pf_m[3] += clock64() - c1; }
         };
-        mbar_wait(q_ready, 0);
+        mbar_wait(q_ready(g), 0);
         tc_fence_after();
         issue_qk(0);
         if (T > 1) issue_qk(1);
         for (int j = 0; j < T; ++j) {
-            const int s = j % ATT_KVS, sb = j & 1;
+            const int s = j % KVS, sb = j & 1;
             long long c0 = 0, c1 = 0;
             if (PROF) c0 = clock64();
-            mbar_wait(p_full(sb), (uint32_t)(j >> 1) & 1u);
-            if (PROF) { c1 = clock64(); pf_hop += c1 - stamp[sb]; }
+            mbar_wait(p_full(g, sb), (uint32_t)(j >> 1) & 1u);
+            if (PROF) { c1 = clock64(); pf_hop += c1 - stamp[2 * g + sb]; }
             tc_fence_after();
             if (lane == 0) {
                 // V tile [64 keys][64 d]: MN-major, 128-byte rows, 8-row groups 1024 B apart, 16 keys per MMA = 2048 B.
@@ -199,7 +222,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 for (int k = 0; k < ATT_BKV / 16; ++k)
                     umma_bf16_ts(tmem_O, tmem + sb * ATT_BKV + k * 8, bd + (uint64_t)(k * 128), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
                 umma_commit(kv_empty(s));
-                umma_commit(o_done);
+                umma_commit(o_done(g));
             }
             __syncwarp();
             if (PROF) { pf_m[0] += c1 - c0; pf_m[1] += clock64() - c1; }
@@ -210,21 +233,27 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             atomicAdd(&g_att_prof[9], (unsigned long long)T);
             atomicAdd(&g_att_prof[12], (unsigned long long)pf_hop);
         }
-    } else {
-        // ===================== softmax + epilogue: thread <-> query row =====================
-        const int q = warp & 3;
+    } else if (warp >= Cfg::SW0) {
+        // ===================== softmax + epilogue of query tile g: thread <-> query row =====================
+        const int g = (warp - Cfg::SW0) >> 2;
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
         const int row = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        {   // Q tile (K-major SWIZZLE_128B rows in smem) -> TMEM columns [192,224): A operand of every QK MMA
-            mbar_wait(q_full, 0);
+        const uint32_t tmem = tmem_base + g * 256;
+        const uint32_t tmem_O = tmem + 128;
+        const uint32_t tmem_L = tmem_O + ATT_D;  // row sums (first of 16 identical columns)
+        const uint32_t tmem_Q = tmem + 208;
+        const int qt = qt0 + g;
+        {   // Q tile (K-major SWIZZLE_128B rows in smem) -> TMEM columns [208,240): A operand of every QK MMA
+            mbar_wait(q_full(g), 0);
             uint32_t qr[32];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const uint4 u = lds128(sQ + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4));
+                const uint4 u = lds128(sQ + g * ATT_Q_BYTES + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4));
                 qr[4 * c + 0] = u.x; qr[4 * c + 1] = u.y; qr[4 * c + 2] = u.z; qr[4 * c + 3] = u.w;
             }
             tmem_st32(tmem_Q + lane_addr, qr);
-            {   // all-ones B tile (bf16 1.0 = 0x3F80): 128 threads x 64 bytes
+            {   // all-ones B tile (bf16 1.0 = 0x3F80): 128 threads x 64 bytes (every query tile's group writes the same values)
                 const uint4 one4 = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) sts128(sOnes + (uint32_t)row * 64u + (uint32_t)(c << 4), one4);
@@ -233,17 +262,18 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(q_ready);
+            if (lane == 0) mbar_arrive(q_ready(g));
         }
         float m_ref = -INFINITY;
         const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
         long long pf_s[4] = {0, 0, 0, 0}, pf_hop = 0;
+        volatile long long* stamp = reinterpret_cast<volatile long long*>(smem_raw + (slot + 16 - raw));
         for (int j = 0; j < T; ++j) {
             const int sb = j & 1;
             long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
             if (PROF) c0 = clock64();
-            mbar_wait(s_full(sb), (uint32_t)(j >> 1) & 1u);
-            if (PROF) { c1 = clock64(); pf_hop += c1 - stamp[2 + sb]; }
+            mbar_wait(s_full(g, sb), (uint32_t)(j >> 1) & 1u);
+            if (PROF) { c1 = clock64(); pf_hop += c1 - stamp[2 * NQ + 2 * g + sb]; }
             tc_fence_after();
             uint32_t sv[64];
             {
@@ -297,7 +327,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             if (__any_sync(0xffffffffu, need)) {  // rare: redo the tile against the new reference
                 const float m_new = need ? mx : m_ref;
                 if (j > 0) {
-                    mbar_wait(o_done, (uint32_t)(j - 1) & 1u);  // PV(j-1) complete: O quiescent (PV(j) waits for our P)
+                    mbar_wait(o_done(g), (uint32_t)(j - 1) & 1u);  // PV(j-1) complete: O quiescent (PV(j) waits for our P)
                     tc_fence_after();
                     const float alpha = need ? exp2f(m_ref - m_new) : 1.0f;
                     {
@@ -325,8 +355,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (PROF && lane == 0) stamp[sb] = clock64();  // last writer = (approximately) the last arriving warp
-            if (lane == 0) mbar_arrive(p_full(sb));
+            if (PROF && lane == 0) stamp[2 * g + sb] = clock64();  // last writer = last arriving warp (approximately)
+            if (lane == 0) mbar_arrive(p_full(g, sb));
             if (PROF) { pf_s[0] += c1 - c0; pf_s[1] += c2 - c1; pf_s[2] += c3 - c2; pf_s[3] += clock64() - c3; }
         }
         if (PROF && lane == 0) {
@@ -335,7 +365,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             atomicAdd(&g_att_prof[13], (unsigned long long)pf_hop);
         }
         // ---- epilogue: O / l -> bf16 ----
-        mbar_wait(o_done, (uint32_t)(T - 1) & 1u);
+        mbar_wait(o_done(g), (uint32_t)(T - 1) & 1u);
         tc_fence_after();
         const uint32_t lsum = tmem_ld1(tmem_L + lane_addr);
         tmem_ld_wait();
@@ -363,7 +393,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, ATT_TMEM_COLS);
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 }  // namespace skb
@@ -393,33 +423,47 @@ extern "C" int skb_flash_attn_bf16(const skb_view* qkv, const skb_view* o, int32
     p.N = N; p.heads = heads; p.C = C; p.T = (N + ATT_BKV - 1) / ATT_BKV;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.out = (__nv_bfloat16*)o->ptr; p.out_pitch = o->pitch;
-    static int poly = -1, prof = 0;
-    if (poly < 0) {  // tuning knob (not part of the ABI): SKB_ATT_POLY in {0, 8, 16, 24, 32}
+    static int poly = -1, nq_force = 0;
+    if (poly < 0) {  // tuning knobs (not part of the ABI): SKB_ATT_POLY in {0, 8, 16}, SKB_ATT_NQ in {1, 2}
         const char* e = getenv("SKB_ATT_POLY");
         poly = e ? atoi(e) : ATT_POLY_DEFAULT;
-        if (poly != 0 && poly != 8 && poly != 16 && poly != 24 && poly != 32) poly = ATT_POLY_DEFAULT;
-        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        e = getenv("SKB_ATT_PROF");  // diagnostics: instrumented variant (skb_debug_attn_prof reads the counters)
-        prof = e ? atoi(e) : 0;
+        if (poly != 0 && poly != 8 && poly != 16) poly = ATT_POLY_DEFAULT;
+        e = getenv("SKB_ATT_NQ");
+        nq_force = e ? atoi(e) : 0;
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2>::SMEM));
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2>::SMEM));
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2>::SMEM));
     }
-    dim3 grid((N + ATT_BQ - 1) / ATT_BQ, heads, B);
+    static int prof = -1;
+    if (prof < 0) {
+        const char* e = getenv("SKB_ATT_PROF");
+        prof = e ? atoi(e) : 0;
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2>::SMEM));
+    }
+    // two query tiles per CTA once the K/V stream is long enough to matter (and 256-row tiles waste little of N)
+    const int nq = nq_force == 1 || nq_force == 2 ? nq_force : (N >= 4096 ? 2 : 1);
     cudaStream_t st = (cudaStream_t)stream;
     if (prof) {
-        flash_attn_kernel<8, true><<<grid, 192, ATT_SMEM, st>>>(tmQ, tmKV, p);
-        SKB_LAUNCH_CHECK();
-        return SKB_OK;
-    }
-    switch (poly) {
-        case 0: flash_attn_kernel<0><<<grid, 192, ATT_SMEM, st>>>(tmQ, tmKV, p); break;
-        case 8: flash_attn_kernel<8><<<grid, 192, ATT_SMEM, st>>>(tmQ, tmKV, p); break;
-        case 24: flash_attn_kernel<24><<<grid, 192, ATT_SMEM, st>>>(tmQ, tmKV, p); break;
-        case 32: flash_attn_kernel<32><<<grid, 192, ATT_SMEM, st>>>(tmQ, tmKV, p); break;
-        default: flash_attn_kernel<16><<<grid, 192, ATT_SMEM, st>>>(tmQ, tmKV, p); break;
+        if (nq == 2) flash_attn_kernel<8, 2, true><<<dim3((N + 2 * ATT_BQ - 1) / (2 * ATT_BQ), heads, B), AttCfg<2>::THREADS, AttCfg<2>::SMEM, st>>>(tmQ, tmKV, p);
+        else flash_attn_kernel<8, 1, true><<<dim3((N + ATT_BQ - 1) / ATT_BQ, heads, B), AttCfg<1>::THREADS, AttCfg<1>::SMEM, st>>>(tmQ, tmKV, p);
+    } else if (nq == 2) {
+        dim3 grid((N + 2 * ATT_BQ - 1) / (2 * ATT_BQ), heads, B);
+        switch (poly) {
+            case 0: flash_attn_kernel<0, 2><<<grid, AttCfg<2>::THREADS, AttCfg<2>::SMEM, st>>>(tmQ, tmKV, p); break;
+            case 16: flash_attn_kernel<16, 2><<<grid, AttCfg<2>::THREADS, AttCfg<2>::SMEM, st>>>(tmQ, tmKV, p); break;
+            default: flash_attn_kernel<8, 2><<<grid, AttCfg<2>::THREADS, AttCfg<2>::SMEM, st>>>(tmQ, tmKV, p); break;
+        }
+    } else {
+        dim3 grid((N + ATT_BQ - 1) / ATT_BQ, heads, B);
+        switch (poly) {
+            case 0: flash_attn_kernel<0, 1><<<grid, AttCfg<1>::THREADS, AttCfg<1>::SMEM, st>>>(tmQ, tmKV, p); break;
+            case 16: flash_attn_kernel<16, 1><<<grid, AttCfg<1>::THREADS, AttCfg<1>::SMEM, st>>>(tmQ, tmKV, p); break;
+            default: flash_attn_kernel<8, 1><<<grid, AttCfg<1>::THREADS, AttCfg<1>::SMEM, st>>>(tmQ, tmKV, p); break;
+        }
     }
     SKB_LAUNCH_CHECK();
     return SKB_OK;

@@ -932,14 +932,15 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
     // than 2.4*(rows) cycles while its MMAs need 2*BN: wide BN amortises the activation rows.
     int BN = 32, NCTA = 1;
     {
-        // CTA pairs are OFF by default: measured on B200 they do not beat the single-CTA kernel (3x3 128->128
-        // @160: 694 vs 742 TFLOP/s) because the kernel is bound by bytes entering the SM through TMA
-        // (~2.4 cycles per 128-byte box row, ~53 B/clk/SM), not by the shared-memory port.  SKB_CONV_PAIR=1
-        // switches them on for experiments (tuning knob, not part of the ABI).
+        // CTA pairs: timed alone (clocks near 1.9 GHz) they do not beat the single-CTA kernel, which is bound by bytes
+        // entering the SM through TMA, not by the shared-memory port.  Inside the full step the board sits on its
+        // 1000 W power cap (SM clock ~1.7 GHz) and the halved weight traffic per CTA buys clock: +0.8-1.8 % images/s
+        // measured on the same box, so pairs are ON by default.  SKB_CONV_PAIR=0 switches them off (tuning knob, not
+        // part of the ABI).
         static int pair_mode = -1;
         if (pair_mode < 0) {
             const char* e = getenv("SKB_CONV_PAIR");
-            pair_mode = e ? atoi(e) : 0;
+            pair_mode = e ? atoi(e) : 1;
         }
         const bool pair_ok = pair_mode != 0 && !upsample2x && taps * Cin >= 256 && m_tiles >= 2;
         double best = 1e30;
