@@ -27,7 +27,7 @@ __device__ __forceinline__ void tma4(uint32_t dst, const CUtensorMap* m, uint32_
 }
 constexpr int STAGES = 6;
 // mode 0: 2-D map, box {64 bf16, rows}; mode 1: 4-D map {64, tw, th, 1} (rows = tw*th) from an NHWC image with C = 128
-__global__ void __launch_bounds__(64, 1) k(const __grid_constant__ CUtensorMap m, int mode, int rows, int tw, int th, int iters, int span, long long* cyc) {
+__global__ void __launch_bounds__(64, 1) k(const __grid_constant__ CUtensorMap m, int mode, int rows, int tw, int th, int iters, int span, int nl, long long* cyc) {
     extern __shared__ uint8_t raw[];
     const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
     const uint32_t bar = base + STAGES * 32768;
@@ -35,7 +35,20 @@ __global__ void __launch_bounds__(64, 1) k(const __grid_constant__ CUtensorMap m
     __syncthreads();
     const uint32_t bytes = rows * 128;
     long long t0 = clock64();
-    if (threadIdx.x == 0) {
+    if (nl > 1 && threadIdx.x < nl) {
+        // nl lanes of one warp issue in lockstep: lane l owns iterations l, l + nl, ... (one instruction = nl boxes)
+        for (int i = threadIdx.x; i < iters; i += nl) {
+            const int st = i % STAGES; const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+            mbar_wait(bar + 8 * (STAGES + st), ph ^ 1);
+            mbar_expect(bar + 8 * st, bytes);
+            const int t = (blockIdx.x * iters + i) % span;
+            if (mode == 0) tma2(base + st * 32768, &m, bar + 8 * st, (t & 31) * 64, (t >> 5) * rows);
+            else {
+                const int nw = 256 / tw, nh = 256 / th;
+                tma4(base + st * 32768, &m, bar + 8 * st, (t & 1) * 64, (t / 2 % nw) * tw, (t / 2 / nw % nh) * th, t / 2 / nw / nh);
+            }
+        }
+    } else if (nl <= 1 && threadIdx.x == 0) {
         int st = 0; uint32_t ph = 0;
         for (int i = 0; i < iters; ++i) {
             mbar_wait(bar + 8 * (STAGES + st), ph ^ 1);
@@ -84,13 +97,15 @@ int main() {
         }
         // distinct tiles in the 512 MB buffer: 2-D: 32 K-chunks x (rows available / rows); 4-D: 2 chunks x tiles per image x 32 images
         const int all_tiles = c.mode == 0 ? 32 * (int)((elems / 2304) / c.rows) : 2 * (256 / c.tw) * (256 / c.th) * 32;
+        for (int nl : {1, 2, 4})
         for (int span : {64, all_tiles}) {  // 64: every CTA re-reads the same few tiles (L2 hits); all: streaming the buffer from HBM
-            k<<<148, 64, STAGES * 32768 + 2048>>>(m, c.mode, c.rows, c.tw, c.th, iters, span, cyc);
+            if (nl > 1 && span != 64) continue;
+            k<<<148, 64, STAGES * 32768 + 2048>>>(m, c.mode, c.rows, c.tw, c.th, iters, span, nl, cyc);
             cudaDeviceSynchronize();
             long long h[148]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
             long long mx = 0; for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
             const double bpc = (double)iters * c.rows * 128 / mx;
-            printf("%-36s span %6d: %7.1f cycles/box  %5.1f B/clk/SM  %.2f cycles/row  (%s)\n", c.name, span, (double)mx / iters, bpc, (double)mx / iters / c.rows, cudaGetErrorString(cudaGetLastError()));
+            printf("%-36s lanes %d span %6d: %7.1f cycles/box  %5.1f B/clk/SM  %.2f cycles/row  (%s)\n", c.name, nl, span, (double)mx / iters, bpc, (double)mx / iters / c.rows, cudaGetErrorString(cudaGetLastError()));
         }
     }
     return 0;
