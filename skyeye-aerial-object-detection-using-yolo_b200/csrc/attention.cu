@@ -13,17 +13,19 @@
 // operand reads and was the co-bottleneck with P and Q staged there).  The softmax is MUFU-bound
 // (64 flop per exponential at head_dim 64); ATT_POLY of every 64 exponentials can be evaluated on the
 // FMA pipes instead (Cody-Waite split + degree-3 polynomial, rel. error 7.5e-5 << bf16), in packed
-// fp32x2 arithmetic.  The softmax denominator is produced by the PV MMA itself (16 all-ones B columns).  MMAs of one CTA execute in issue order, which is what lets QK(j+2) reuse the
-// S/P buffer of tile j right after PV(j) has been issued.
+// fp32x2 arithmetic.  The softmax denominator is produced by the PV MMA itself (16 all-ones B columns).  MMAs issued
+// by one thread execute in issue order, which is what lets QK(j+2) reuse the S/P buffer of tile j right after PV(j)
+// has been issued.
 // The in_proj output [B, N, 3C] is read in place: one 3-D tensor map {channel, token, image} serves
 // Q, K and V (different channel coordinates), ragged N is TMA zero fill + a -inf mask on the last tile.
 // NQ = 1 (short sequences): 2 CTAs are resident per SM (89 KB smem, 256 TMEM columns each) so one CTA's softmax
 // overlaps the other's MMAs; warp roles 0 = TMA producer, 1 = MMA issuer, 2..5 = softmax/epilogue.
 // NQ = 2 (N >= 4096): ONE CTA per SM owns two query tiles that share the K/V stream; each tile has its own MMA-issuing
-// warp (1, 2), softmax warpgroup (4..7, 8..11) and 256 TMEM columns, and the two run unsynchronised.  Kernel time alone
-// is the same as two NQ = 1 CTAs (profiles/r1m_attention_pipeline.md), but the K/V traffic L2 -> shared memory and the
-// TMA writes are halved, and under the board's 1000 W power cap (which holds the SM clock near 1.7 GHz for the whole
-// step) that buys clock: +1.6 % images/s on the full step, measured on the same box.
+// warp (1, 2), softmax warpgroup (4..7, 8..11) and 256 TMEM columns, and the two run unsynchronised.  Timed alone this
+// form is 0-5 % slower than two NQ = 1 CTAs (profiles/r1m_attention_pipeline.md, r1q_ncu_hot_kernels.md), but the K/V
+// traffic L2 -> shared memory and the TMA writes are halved, and under the board's 1000 W power cap (which holds the SM
+// clock near 1.7-1.8 GHz for the whole step) that buys clock: +2.1 % images/s on the full step, measured on the same box
+// in one call.
 #include <math.h>
 #include <stdlib.h>
 
@@ -39,8 +41,7 @@ constexpr int ATT_ON = ATT_D + 16;                  // PV accumulator width: 64 
 constexpr int ATT_POLY_DEFAULT = 8;                 // exponentials per 64 evaluated on the FMA pipes (0, 8, 16, 24, 32)
 
 // NQ = query tiles (of 128 rows) per CTA.  NQ = 1: 192 threads, 2 CTAs per SM.  NQ = 2: ONE CTA per SM whose two
-// query tiles share the K/V stream in shared memory -- the K/V traffic from L2 (which alone takes half of the NQ = 1
-// kernel's time at N = 25600: 12.7 TB/s, the L2 limit) and the TMA writes into shared memory are halved.  Each query
+// query tiles share the K/V stream in shared memory (half the K/V bytes from L2 and half the TMA writes).  Each query
 // tile has its own MMA-issuing warp, softmax warpgroup and 256 TMEM columns; the two run unsynchronised.
 template <int NQ>
 struct AttCfg {
