@@ -152,31 +152,42 @@ __global__ void letterbox_kernel(const uint8_t* __restrict__ src, int h0, int w0
 // ---------------------------------------------------------------------------------------------
 // MaxPool2d(5, 1, 2) on bf16 NHWC (padding acts as -inf)
 // ---------------------------------------------------------------------------------------------
+// One thread per (image, column x, group of 8 channels) walks down the column and keeps the horizontal 5-maxima of the
+// five most recent rows in registers: 5 loads per output instead of 25 (the 25-load form was issue-bound: 69 % of the
+// issue slots at 1.0 TB/s).  bf16 max is exact, so the result is bit-identical.
 __global__ void maxpool5_kernel(const __nv_bfloat16* __restrict__ x, long xpitch, __nv_bfloat16* __restrict__ y, long ypitch,
                                 int N, int H, int W, int C8) {
-    const long total = (long)N * H * W * C8;
+    const long total = (long)N * W * C8;
+    const __nv_bfloat162 ninf = __float2bfloat162_rn(-INFINITY);
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int g = (int)(i % C8);
-        long pix = i / C8;
-        const int px = (int)(pix % W);
-        const int py = (int)((pix / W) % H);
-        const int n = (int)(pix / ((long)W * H));
-        __nv_bfloat162 m[4];
-        const __nv_bfloat162 ninf = __float2bfloat162_rn(-INFINITY);
-        m[0] = m[1] = m[2] = m[3] = ninf;
-        for (int dy = -2; dy <= 2; ++dy) {
-            const int yy = py + dy;
-            if (yy < 0 || yy >= H) continue;
-            for (int dx = -2; dx <= 2; ++dx) {
-                const int xx = px + dx;
-                if (xx < 0 || xx >= W) continue;
-                const uint4 u = *reinterpret_cast<const uint4*>(x + (((long)n * H + yy) * W + xx) * xpitch + g * 8);
+        const long t = i / C8;
+        const int px = (int)(t % W);
+        const int n = (int)(t / W);
+        const int xa = max(px - 2, 0), xb = min(px + 2, W - 1);
+        const __nv_bfloat16* col = x + ((long)n * H * W) * xpitch + g * 8;
+        auto rowmax = [&](int r, __nv_bfloat162 (&m)[4]) {
+            m[0] = m[1] = m[2] = m[3] = ninf;
+            if (r < 0 || r >= H) return;
+            const __nv_bfloat16* rowp = col + ((long)r * W) * xpitch;
+            for (int xx = xa; xx <= xb; ++xx) {
+                const uint4 u = *reinterpret_cast<const uint4*>(rowp + (long)xx * xpitch);
                 const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&u);
                 m[0] = __hmax2(m[0], v[0]); m[1] = __hmax2(m[1], v[1]);
                 m[2] = __hmax2(m[2], v[2]); m[3] = __hmax2(m[3], v[3]);
             }
+        };
+        __nv_bfloat162 r0[4], r1[4], r2[4], r3[4], r4[4];  // horizontal maxima of rows py-2 .. py+2
+        rowmax(-2, r0); rowmax(-1, r1); rowmax(0, r2); rowmax(1, r3);
+        for (int py = 0; py < H; ++py) {
+            rowmax(py + 2, r4);
+            __nv_bfloat162 m[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) m[q] = __hmax2(__hmax2(__hmax2(r0[q], r1[q]), __hmax2(r2[q], r3[q])), r4[q]);
+            *reinterpret_cast<uint4*>(y + (((long)n * H + py) * W + px) * ypitch + g * 8) = *reinterpret_cast<uint4*>(m);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { r0[q] = r1[q]; r1[q] = r2[q]; r2[q] = r3[q]; r3[q] = r4[q]; }
         }
-        *reinterpret_cast<uint4*>(y + pix * ypitch + g * 8) = *reinterpret_cast<uint4*>(m);
     }
 }
 
@@ -586,8 +597,8 @@ extern "C" int skb_maxpool5_bf16(const skb_view* x, const skb_view* y, void* str
     if (rc != SKB_OK) return rc;
     SKB_REQUIRE(view_ok_bf16(x) && view_ok_bf16(y), SKB_ERR_ARG, "maxpool5: bad view");
     SKB_REQUIRE(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c, SKB_ERR_ARG, "maxpool5: shape mismatch");
-    const long total = (long)x->n * x->h * x->w * (x->c / 8);
-    maxpool5_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x->ptr, x->pitch, (__nv_bfloat16*)y->ptr,
+    const long total = (long)x->n * x->w * (x->c / 8);  // one thread per (image, column, 8 channels)
+    maxpool5_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x->ptr, x->pitch, (__nv_bfloat16*)y->ptr,
                                                                              y->pitch, x->n, x->h, x->w, x->c / 8);
     SKB_LAUNCH_CHECK();
     return SKB_OK;

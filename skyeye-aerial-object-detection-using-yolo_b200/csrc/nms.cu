@@ -251,6 +251,7 @@ nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict_
     __shared__ int s_nsurv, s_kept;
     __shared__ float cx1[NMS_THREADS], cy1[NMS_THREADS], cx2[NMS_THREADS], cy2[NMS_THREADS], car[NMS_THREADS];
     __shared__ float crow[NMS_THREADS][7];
+    extern __shared__ unsigned int smask[];  // [NMS_THREADS][NMS_THREADS / 32] pairwise suppression bits of a chunk (32 KB)
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -288,23 +289,46 @@ nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict_
 #pragma unroll
         for (int q = 0; q < 7; ++q) crow[tid][q] = c.row[q];
         __syncthreads();
-        // phase B: survivors in order, one warp, each against the boxes kept within THIS chunk
+        // phase B1: pairwise suppression masks among this chunk's survivors, in parallel.  Row s (survivor position s) has
+        // bit j of word j / 32 set iff survivor j < s overlaps s by more than the threshold (same arithmetic as everywhere:
+        // a zero intersection gives 0 or NaN, never > thr, so it short-cuts the division).
+        {
+            const int ns = s_nsurv;
+            if (tid < ns) {
+                const int t = surv[tid];
+                const float ax1 = cx1[t], ay1 = cy1[t], ax2 = cx2[t], ay2 = cy2[t], aar = car[t];
+                for (int w = 0; w <= (tid >> 5); ++w) {
+                    const int j0 = w * 32, j1 = min(j0 + 32, tid);
+                    unsigned int m = 0;
+                    for (int j = j0; j < j1; ++j) {
+                        const int u = surv[j];
+                        const float xx1 = fmaxf(cx1[u], ax1), yy1 = fmaxf(cy1[u], ay1);
+                        const float xx2 = fminf(cx2[u], ax2), yy2 = fminf(cy2[u], ay2);
+                        if (xx2 > xx1 && yy2 > yy1 &&
+                            iou_gt(cx1[u], cy1[u], cx2[u], cy2[u], car[u], ax1, ay1, ax2, ay2, aar, p.iou))
+                            m |= 1u << (j - j0);
+                    }
+                    smask[tid * (NMS_THREADS / 32) + w] = m;
+                }
+            }
+        }
+        __syncthreads();
+        // phase B2: greedy resolution in order by one warp: lane w holds word w of the set kept within this chunk
         if (warp == 0) {
             const int ns = s_nsurv;
             int kept = kept0;
+            unsigned int kw = 0;
             for (int s = 0; s < ns && kept < p.max_det; ++s) {
-                const int t = surv[s];
-                const float ax1 = cx1[t], ay1 = cy1[t], ax2 = cx2[t], ay2 = cy2[t], aar = car[t];
-                bool sup = false;
-                for (int k = kept0 + lane; k < kept; k += 32)
-                    if (iou_gt(kx1[k], ky1[k], kx2[k], ky2[k], kar[k], ax1, ay1, ax2, ay2, aar, p.iou)) { sup = true; break; }
-                if (!__any_sync(0xffffffffu, sup)) {
-                    if (lane == 0) { kx1[kept] = ax1; ky1[kept] = ay1; kx2[kept] = ax2; ky2[kept] = ay2; kar[kept] = aar; }
+                const unsigned int m = lane <= (s >> 5) ? smask[s * (NMS_THREADS / 32) + lane] : 0u;
+                if (!__any_sync(0xffffffffu, (m & kw) != 0u)) {
+                    const int t = surv[s];
+                    if (lane == 0) { kx1[kept] = cx1[t]; ky1[kept] = cy1[t]; kx2[kept] = cx2[t]; ky2[kept] = cy2[t]; kar[kept] = car[t]; }
                     if (lane < 7) out[((long)b * p.max_det + kept) * 7 + lane] = crow[t][lane];
+                    if (lane == (s >> 5)) kw |= 1u << (s & 31);
                     ++kept;
-                    __syncwarp();
                 }
             }
+            __syncwarp();
             if (lane == 0) s_kept = kept;
         }
         __syncthreads();
@@ -409,7 +433,13 @@ extern "C" int skb_nms_batched_f32(const float* pred, int32_t b, int32_t n, int3
     BatchedParams bp;
     bp.pred = pred; bp.B = b; bp.N = n; bp.nc = nc; bp.no = nc + 5; bp.iou = iou_thr; bp.agnostic = agnostic; bp.multi_label = multi_label;
     bp.compat = compat; bp.max_det = max_det; bp.capacity = (int)cap;
-    nms_keptlist_kernel<<<b, NMS_THREADS, 0, st>>>(bp, ws.keys_out, ws.count, out, out_count);
+    constexpr int kMaskBytes = NMS_THREADS * (NMS_THREADS / 32) * (int)sizeof(unsigned int);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SKB_CUDA(cudaFuncSetAttribute(nms_keptlist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaskBytes));
+        attr_set = true;
+    }
+    nms_keptlist_kernel<<<b, NMS_THREADS, kMaskBytes, st>>>(bp, ws.keys_out, ws.count, out, out_count);
     SKB_LAUNCH_CHECK();
     return SKB_OK;
 }
