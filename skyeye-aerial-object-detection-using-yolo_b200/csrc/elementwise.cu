@@ -70,13 +70,14 @@ __global__ void focus_kernel(const T* __restrict__ img, int N, int H, int W, __n
 
 // Same space-to-depth into the padded 16-channel scratch of skb_focus_conv_bf16: row = [0 | Wo pixels | 0 0 0]
 template <typename T>
+// One CTA per output row (n, oy): no per-element index division (the flat 64-bit i % Wp, i / Wp form spent most of its
+// issue slots on it: 1.7 TB/s).
 __global__ void focus_pad_kernel(const T* __restrict__ img, int N, int H, int W, __nv_bfloat16* __restrict__ y) {
     const int Ho = H / 2, Wo = W / 2, Wp = Wo + 4;
-    const long total = (long)N * Ho * Wp;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int col = (int)(i % Wp);
-        const int oy = (int)((i / Wp) % Ho);
-        const int n = (int)(i / ((long)Wp * Ho));
+    const int oy = (int)(blockIdx.x % (unsigned int)Ho);
+    const int n = (int)(blockIdx.x / (unsigned int)Ho);
+    for (int col = threadIdx.x; col < Wp; col += blockDim.x) {
+        const long i = ((long)n * Ho + oy) * Wp + col;
         uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
         const int ox = col - 1;
         if (ox >= 0 && ox < Wo) {
@@ -156,14 +157,18 @@ __global__ void letterbox_kernel(const uint8_t* __restrict__ src, int h0, int w0
 // five most recent rows in registers: 5 loads per output instead of 25 (the 25-load form was issue-bound: 69 % of the
 // issue slots at 1.0 TB/s).  bf16 max is exact, so the result is bit-identical.
 __global__ void maxpool5_kernel(const __nv_bfloat16* __restrict__ x, long xpitch, __nv_bfloat16* __restrict__ y, long ypitch,
-                                int N, int H, int W, int C8) {
-    const long total = (long)N * W * C8;
+                                int N, int H, int W, int C8, int segs) {
+    const long total = (long)N * segs * W * C8;  // a column is cut into `segs` row segments (more threads in flight)
+    const int rows_per = (H + segs - 1) / segs;
     const __nv_bfloat162 ninf = __float2bfloat162_rn(-INFINITY);
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int g = (int)(i % C8);
-        const long t = i / C8;
+        long t = i / C8;
         const int px = (int)(t % W);
-        const int n = (int)(t / W);
+        t /= W;
+        const int seg = (int)(t % segs);
+        const int n = (int)(t / segs);
+        const int y0 = seg * rows_per, y1 = min(H, y0 + rows_per);
         const int xa = max(px - 2, 0), xb = min(px + 2, W - 1);
         const __nv_bfloat16* col = x + ((long)n * H * W) * xpitch + g * 8;
         auto rowmax = [&](int r, __nv_bfloat162 (&m)[4]) {
@@ -178,8 +183,8 @@ __global__ void maxpool5_kernel(const __nv_bfloat16* __restrict__ x, long xpitch
             }
         };
         __nv_bfloat162 r0[4], r1[4], r2[4], r3[4], r4[4];  // horizontal maxima of rows py-2 .. py+2
-        rowmax(-2, r0); rowmax(-1, r1); rowmax(0, r2); rowmax(1, r3);
-        for (int py = 0; py < H; ++py) {
+        rowmax(y0 - 2, r0); rowmax(y0 - 1, r1); rowmax(y0, r2); rowmax(y0 + 1, r3);
+        for (int py = y0; py < y1; ++py) {
             rowmax(py + 2, r4);
             __nv_bfloat162 m[4];
 #pragma unroll
@@ -567,11 +572,11 @@ extern "C" int skb_focus_nchw_u8(const uint8_t* img, int32_t n, int32_t h, int32
 
 namespace skb {
 int launch_focus_pad(const void* img, int img_dtype, int n, int h, int w, void* scratch, cudaStream_t st) {
-    const long total = (long)n * (h / 2) * (w / 2 + 4);
+    const int rows = n * (h / 2);  // one CTA per padded output row
     if (img_dtype == SKB_F32)
-        focus_pad_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)img, n, h, w, (__nv_bfloat16*)scratch);
+        focus_pad_kernel<float><<<rows, 256, 0, st>>>((const float*)img, n, h, w, (__nv_bfloat16*)scratch);
     else
-        focus_pad_kernel<uint8_t><<<grid_for(total, 256), 256, 0, st>>>((const uint8_t*)img, n, h, w, (__nv_bfloat16*)scratch);
+        focus_pad_kernel<uint8_t><<<rows, 256, 0, st>>>((const uint8_t*)img, n, h, w, (__nv_bfloat16*)scratch);
     SKB_LAUNCH_CHECK();
     return SKB_OK;
 }
@@ -597,9 +602,10 @@ extern "C" int skb_maxpool5_bf16(const skb_view* x, const skb_view* y, void* str
     if (rc != SKB_OK) return rc;
     SKB_REQUIRE(view_ok_bf16(x) && view_ok_bf16(y), SKB_ERR_ARG, "maxpool5: bad view");
     SKB_REQUIRE(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c, SKB_ERR_ARG, "maxpool5: shape mismatch");
-    const long total = (long)x->n * x->w * (x->c / 8);  // one thread per (image, column, 8 channels)
+    const int segs = x->h >= 32 ? 4 : (x->h >= 8 ? 2 : 1);
+    const long total = (long)x->n * segs * x->w * (x->c / 8);  // one thread per (image, row segment, column, 8 channels)
     maxpool5_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x->ptr, x->pitch, (__nv_bfloat16*)y->ptr,
-                                                                             y->pitch, x->n, x->h, x->w, x->c / 8);
+                                                                             y->pitch, x->n, x->h, x->w, x->c / 8, segs);
     SKB_LAUNCH_CHECK();
     return SKB_OK;
 }
