@@ -325,8 +325,9 @@ def run_b200(args):
                 "launches_per_step": d["launches"] // nrep, "avg_launch_ms": d["ms"] / d["calls"],
                 "share_of_step": table[dom]["share"],
                 "algorithmic_flops_per_launch": d["flops"] / d["calls"], "algorithmic_bytes_per_launch": d["bytes"] / d["calls"],
-                "note": "attention at head_dim 64 is bound by the MUFU pipe (16 ex2/clk/SM measured, 256 flop per exponential): "
-                        "<= ~1.12 PFLOP/s at 1.85 GHz" if dom == "attention" else ""}
+                "note": "attention at head_dim 64: the MUFU pipe (16 ex2/clk/SM measured, 256 flop per exponential) caps it at "
+                        "~1.12 PFLOP/s at 1.85 GHz; measured co-limits are the MMA-issuing thread (~100 cycles per tcgen05.mma) and "
+                        "~100-cycle mbarrier round trips (profiles/r1m_attention_pipeline.md)" if dom == "attention" else ""}
 
     # end-to-end through the public API with host buffers
     for _ in range(2):
