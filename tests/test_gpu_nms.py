@@ -75,3 +75,29 @@ def test_wrapper_stress_config5_sample():
         ref = onms.non_max_suppression(p, **kw)
         for a, b in zip(out, ref):
             assert np.array_equal(a.cpu().numpy(), b)
+
+
+def test_wrapper_dense_clusters_many_chunks_bit_exact():
+    """Heavily overlapping candidates: hundreds of 512-candidate chunks are walked before max_det boxes are kept, so the
+    kept-list kernel's phase A (against earlier chunks), its pairwise bit masks and the greedy resolution are all exercised
+    with real suppression (the stress case above keeps almost every candidate of its first chunk)."""
+    from skyeye.utils.metrics import non_max_suppression
+    g = cases.rng("dense-clusters")
+    B, N, nc = 3, 20000, 4
+    p = np.empty((B, N, 5 + nc), dtype=np.float32)
+    centers = g.random((B, 60, 2), dtype=np.float32) * 1200 + 40
+    which = g.integers(0, 60, (B, N))
+    for b in range(B):
+        p[b, :, 0:2] = centers[b, which[b]] + g.normal(0, 3.0, (N, 2)).astype(np.float32)
+    p[..., 2:4] = (30 + g.random((B, N, 2), dtype=np.float32) * 10)
+    for b in range(B):
+        p[b, :, 4] = g.permutation(np.linspace(0.3, 0.999, N)).astype(np.float32)
+    p[..., 5:] = g.random((B, N, nc), dtype=np.float32) * 0.5 + 0.5
+    for kw in (dict(conf_threshold=0.25, iou_threshold=0.45), dict(conf_threshold=0.25, iou_threshold=0.3, agnostic=True),
+               dict(conf_threshold=0.25, iou_threshold=0.6, max_detections=1000)):
+        # compat="fixed": corner boxes (the reference-compat rows treat (cx, cy, w, h) as corners, where nothing overlaps)
+        out = non_max_suppression(torch.from_numpy(p).cuda(), compat="fixed", **kw)
+        ref = onms.non_max_suppression(p, compat="fixed", **kw)
+        for a, r in zip(out, ref):
+            assert a.shape[0] == r.shape[0] and a.shape[0] > 30
+            assert np.array_equal(a.cpu().numpy(), r)
