@@ -258,21 +258,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int tile = work0; tile < p.total_tiles; tile += wstride) {
                 int nb, w0, h0, n0;
                 decode_tile<NCTA>(p, tile, cta_rank, nb, w0, h0, n0);
+                // tap / chunk counters and the current tap's coordinates live in registers: the per-iteration
+                // it / cchunks division and four dynamically indexed parameter loads cost ~200 of the ~630 cycles a
+                // k-iteration takes this thread (scripts/trace_focus.py), and the producer paces every BN <= 256 layer.
+                int tap = 0, cc = 0;
+                int t_coff = p.tap_coff[0], t_dw = p.tap_dw[0], t_ph = p.tap_ph[0], t_dh = p.tap_dh[0];
                 for (int it = 0; it < p.k_iters; ++it) {
                     mbar_wait(empty(stage), phase ^ 1);
                     // pair: both CTAs' bytes complete on the LEADER's full barrier (its single arrival carries the total)
                     const uint32_t fb = NCTA == 2 ? mapa_shared(full(stage), 0) : full(stage);
                     if (loads_a) {
-                        const int tap = it / p.cchunks;
-                        const int cc = it - tap * p.cchunks;
                         SKB_TR(0, it);
                         if (leader) mbar_expect_tx(full(stage), (uint32_t)NCTA * (uint32_t)(p.a_box_bytes + Cfg::B_BYTES));
                         if (NCTA == 2)
-                            tma_load_5d_pair(sA0 + stage * Cfg::A_BYTES, &tmA, fb, p.tap_coff[tap] + cc * BK,
-                                             w0 + p.tap_dw[tap], p.tap_ph[tap], h0 + p.tap_dh[tap], n0);
+                            tma_load_5d_pair(sA0 + stage * Cfg::A_BYTES, &tmA, fb, t_coff + cc * BK, w0 + t_dw, t_ph, h0 + t_dh, n0);
                         else
-                            tma_load_5d(sA0 + stage * Cfg::A_BYTES, &tmA, fb, p.tap_coff[tap] + cc * BK,
-                                        w0 + p.tap_dw[tap], p.tap_ph[tap], h0 + p.tap_dh[tap], n0);
+                            tma_load_5d(sA0 + stage * Cfg::A_BYTES, &tmA, fb, t_coff + cc * BK, w0 + t_dw, t_ph, h0 + t_dh, n0);
+                        if (++cc == p.cchunks) {  // next tap: its coordinates load under the next barrier wait
+                            cc = 0;
+                            if (++tap < 9) { t_coff = p.tap_coff[tap]; t_dw = p.tap_dw[tap]; t_ph = p.tap_ph[tap]; t_dh = p.tap_dh[tap]; }
+                        }
                     } else {
                         if (NCTA == 2) tma_load_2d_pair(sB0 + stage * Cfg::B_BYTES, &tmB, fb, it * BK, nb * BN + cta_rank * (BN / 2));
                         else tma_load_2d(sB0 + stage * Cfg::B_BYTES, &tmB, fb, it * BK, nb * BN);
