@@ -502,7 +502,7 @@ cla_apply_kernel(const float* __restrict__ s, const float* __restrict__ st, cons
 // outstanding (the one-token version was latency-bound at 1.5 TB/s).
 // ---------------------------------------------------------------------------------------------
 template <int VPL, int TPI>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, VPL <= 2 ? 4 : 2)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, long xpitch, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, long ntok, int C, __nv_bfloat16* __restrict__ y, long ypitch) {
     const int lane = threadIdx.x & 31;
