@@ -67,28 +67,51 @@ def synthetic_images(batch, size, seed):
 # ------------------------------------------------------------------------------------------------
 # CPU oracle leg (cpu_baseline and --impl reference)
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_run(variant, size, n_images, steps, warmup, seed=1234):
+WEIGHTS = ("random 'trained-like' weights, seed 0 (oracle.model.make_calibrated_state_dict: reference init distributions, "
+           "BN statistics calibrated on seeded noise images, residual-branch BN scale 0.25); the SAME state dict in both arms")
+
+
+def shared_state_dict(variant):
+    """The one state dict both arms load (weight recipe = test infrastructure under oracle/; building the weights is
+    not part of any timed region)."""
+    from oracle import model as om
+    cfg = om.get_cfg(variant)
+    return om.make_calibrated_state_dict(cfg, 0), cfg
+
+
+def workload_config(variant, size, batch):
+    """Identical in both arms (the driver compares the two lines' configs)."""
+    return {"workload": f"{variant} {size}x{size} batch {batch}/GPU: forward (CSP backbone, PAN neck, CLA, transformer heads) + decode + "
+                        f"NMS(conf {CONF}, iou {IOU}, max_det {MAX_DET})",
+            "weights": WEIGHTS, "input": "synthetic uint8 images, PCG64 seed 1234 + rank",
+            "sharding": f"images by rank, {batch} per GPU, no data-path collective"}
+
+
+def cpu_oracle_run(variant, size, n_images, steps, warmup, seed=1234, sd=None, cfg=None):
     """Times the oracle port (oracle/model.py + oracle/nms.py: the reference's PyTorch fp32 path and
-    torchvision-style NMS restated) on this box's host cores. Returns (images/s, cores, seconds/step)."""
+    torchvision-style NMS restated) on this box's host cores.
+    Returns (images/s, cores, seconds/step, (det, raws, nms_rows) of the last pass)."""
     import torch
     from oracle import model as om
     from oracle import nms as onms
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = om.get_cfg(variant)
-    sd = om.make_state_dict(cfg, 0)
+    if sd is None:
+        sd, cfg = shared_state_dict(variant)
     x = torch.from_numpy(synthetic_images(n_images, size, seed)).float() / 255.0
     onms.build()
     ts = []
+    last = None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        det, _ = om.forward(x, sd, cfg)
-        onms.non_max_suppression(det.numpy(), CONF, IOU, max_detections=MAX_DET)
+        det, raws = om.forward(x, sd, cfg)
+        rows = onms.non_max_suppression(det.numpy(), CONF, IOU, max_detections=MAX_DET)
         dt = time.perf_counter() - t0
+        last = (det, raws, rows)
         if i >= warmup:
             ts.append(dt)
     total = sum(ts)
-    return n_images * len(ts) / total, cores, total / len(ts)
+    return n_images * len(ts) / total, cores, total / len(ts), last
 
 
 def run_reference(args):
@@ -96,13 +119,14 @@ def run_reference(args):
     if rank != 0:
         return
     n_img = 1  # bounded sample: one image of the 16-image batch per step
-    value, cores, sec = cpu_oracle_run(args.variant, args.size, n_img, args.steps, args.warmup)
+    value, cores, sec, _ = cpu_oracle_run(args.variant, args.size, n_img, args.steps, args.warmup)
     sample = f"{n_img} image of the {args.batch}-image batch per step, {args.variant} {args.size}x{args.size} fp32, forward+decode+NMS"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.variant} {args.size}x{args.size} batch {args.batch}/GPU forward+decode+NMS (CPU oracle port of the reference path)"},
+        "config": workload_config(args.variant, args.size, args.batch),
+        "run": {"arm": "CPU oracle port of the reference path (fp32, PyTorch eager + C NMS)", "sample": sample},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -181,8 +205,9 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     _native.check(_native.lib().skb_device_check(), "skb_device_check")
 
-    torch.manual_seed(0)
-    model = construct_model(f"{args.variant}.yaml")  # random-init weights of the named architecture (reference init)
+    sd, ocfg = shared_state_dict(args.variant)       # the same weights the CPU arm runs (built outside every timed region)
+    model = construct_model(f"{args.variant}.yaml")
+    model.load_state_dict(sd, strict=True)
     model = model.to(dev).eval()
     model.reuse_output_buffers = True
     model.use_cuda_graph = not args.no_graph  # the forward plan (no host syncs) is captured once per input shape and replayed
@@ -366,27 +391,49 @@ def run_b200(args):
     act_gb = sum(v.t.numel() * v.t.element_size() for v in plan.keep if isinstance(v, View)) / 1e9
 
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, sec = cpu_oracle_run(args.variant, S, 1, 1, 1)
+        # GPU result for image 0 of the batch (state left by the last resident step), then the CPU leg on the same image + weights
+        step_resident()
+        torch.cuda.synchronize()
+        g_raws = [r[0].float().cpu() for r in plan.raw_out]
+        g_det0 = plan.det[:1].float().cpu()
+        g_rows = nms_out[0, :int(nms_cnt[0])].cpu().numpy()
+        v, cores, sec, (o_det, o_raws, o_rows) = cpu_oracle_run(args.variant, S, 1, 1, 1, seed=1234 + rank, sd=sd, cfg=ocfg)
         cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                "sample": f"1 image of the {B}-image batch (1 warm-up + 1 timed pass, {sec:.1f} s), {args.variant} {S}x{S} fp32 oracle forward+decode+NMS"}
+        import numpy as np
+        from oracle import nms as onms
+        lv = []
+        for a, b in zip(g_raws, o_raws):
+            b = b[0]
+            lv.append({"max_rel": float((a - b).abs().max() / b.abs().max()), "rms": float((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt())})
+        ref_rows = onms.non_max_suppression(g_det0.numpy(), CONF, IOU, max_detections=MAX_DET)[0]   # oracle NMS on the GPU's own detections
+        dec = ((g_det0[..., 4:] > 0.5) == (o_det[..., 4:] > 0.5)).float().mean()
+        parity = {"vs": "fp32 CPU oracle, image 0 of the batch, same state dict", "max_rel": max(l["max_rel"] for l in lv),
+                  "rms": max(l["rms"] for l in lv), "per_level": lv,
+                  "nms_rows_equal": bool(g_rows.shape == ref_rows.shape and np.array_equal(g_rows, ref_rows)),
+                  "nms_rows": int(g_rows.shape[0]), "sigmoid_decisions_agree": float(dec),
+                  "note": "max_rel / rms of the raw head logits relative to per-level max |logit| / rms logit (bf16 activations vs fp32 reference "
+                          "arithmetic; tests/test_gpu_teacher_forced.py holds the per-launch 1e-3 gate); nms_rows_equal = GPU NMS rows bit-equal to "
+                          "the oracle NMS on identical detections"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"{args.variant} {S}x{S} batch {B}/GPU: forward (CSP backbone, PAN neck, CLA, transformer heads) + decode + NMS(conf {CONF}, iou {IOU}, max_det {MAX_DET})",
-                       "weights": "random-init (reference _initialize_weights distributions, seed 0), BN folded, bf16",
-                       "sharding": f"images by rank, {B} per GPU, no data-path collective",
-                       "launch": "CUDA graph replay of the forward plan + NMS launches" if model.use_cuda_graph else "per-kernel launches",
-                       "l2": f"inputs+activations per step {act_gb:.1f} GB >> 126 MB L2 (no flush needed)"},
+            "config": workload_config(args.variant, S, B),
+            "run": {"arm": "B200 native path (BN folded, bf16 operands, fp32 accumulate)",
+                    "launch": "CUDA graph replay of the forward plan + NMS launches" if model.use_cuda_graph else "per-kernel launches",
+                    "l2": f"inputs+activations per step {act_gb:.1f} GB >> 126 MB L2 (no flush needed)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(host.numel()),
                     "d2h_bytes_per_step": int(out_host.numel() * 4 + cnt_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "parity": parity,
             "latency_b1": latency,
             "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in table.items()},
         }

@@ -17,3 +17,10 @@ def run_module(mod, x: torch.Tensor) -> torch.Tensor:
     out = mod.lower(plan, xin)
     plan.run()
     return out.nchw().float()
+
+
+def ref(mod, suffix: str = ""):
+    """Reference state-dict path of ``mod`` (set by SkyEyeDetector._build_plan from named_modules) + suffix; None when
+    the module is lowered stand-alone.  Labels the plan's outputs for Plan.run_teacher_forced."""
+    r = getattr(mod, "_ref", None)
+    return None if r is None else r + suffix

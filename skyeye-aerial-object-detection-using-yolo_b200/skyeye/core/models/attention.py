@@ -54,7 +54,8 @@ class CombinedAttention(nn.Module):
             out = plan.buf(x.n, x.h, x.w, x.c)
         ws = plan.ws(L.E.N.lib().skb_cbam_workspace_bytes(x.n, x.h, x.w, x.c))
         plan.keep += [w0, w1, w7]
-        plan.add(name, lambda s: L.E.cbam(x, w0, w1, w7, out, ws, s), "cbam", 0.0, 2.0 * x.n * x.h * x.w * x.c * 4, 4)
+        plan.add(name, lambda s: L.E.cbam(x, w0, w1, w7, out, ws, s), "cbam", 0.0, 2.0 * x.n * x.h * x.w * x.c * 4, 4,
+                 outs=[dict(view=out, label=L.ref(self))])
         return out
 
     def forward(self, x):
@@ -78,22 +79,24 @@ class CrossLayerAttention(nn.Module):
         dev = plan.device
         cq, cv = self.query_channels, self.value_channels
         q = plan.buf(query.n, query.h, query.w, cq)
-        plan.conv(name + ".q", query, PackedConv(self.query_projection.weight, self.query_projection.bias, dev), q, 1, ACT_NONE)
+        plan.conv(name + ".q", query, PackedConv(self.query_projection.weight, self.query_projection.bias, dev), q, 1, ACT_NONE,
+                  label=L.ref(self, ".q"))
         kv = plan.buf(key.n, key.h, key.w, cq + cv)
         pk = PackedConv(self.key_projection.weight, self.key_projection.bias, dev)
         pv = PackedConv(self.value_projection.weight, self.value_projection.bias, dev)
-        plan.conv(name + ".k|v", key, PackedConv.concat([pk, pv]), kv, 1, ACT_NONE)
+        plan.conv(name + ".k|v", key, PackedConv.concat([pk, pv]), kv, 1, ACT_NONE,
+                  label=[(0, cq, L.ref(self, ".k")), (cq, cq + cv, L.ref(self, ".v"))])
         o = plan.buf(query.n, query.h, query.w, cv)
         ws = plan.ws(L.E.N.lib().skb_cla_workspace_bytes(query.n, query.h, query.w, self.heads))
         k, v = kv.slice(0, cq), kv.slice(cq, cq + cv)
         r2 = float(self.region_size * self.region_size)
         npx = query.n * query.h * query.w
         plan.add(name + ".core", lambda s: L.E.cla_core(q, k, v, o, self.heads, self.scale, r2, ws, s), "cla", 0.0,
-                 2.0 * npx * (cq + cv) + 2.0 * (npx // 4) * (cq + cv), 3)
+                 2.0 * npx * (cq + cv) + 2.0 * (npx // 4) * (cq + cv), 3, outs=[dict(view=o, label=L.ref(self, ".core"))])
         if out is None:
             out = plan.buf(query.n, query.h, query.w, self.output_projection.out_channels)
         po = PackedConv(self.output_projection.weight, self.output_projection.bias, dev)
-        return plan.conv(name + ".out", o, po, out, 1, ACT_NONE, residual)
+        return plan.conv(name + ".out", o, po, out, 1, ACT_NONE, residual, label=L.ref(self, ".out"))
 
     def forward(self, query, key):
         if not query.is_cuda:
@@ -124,24 +127,29 @@ class TransformerLayer(nn.Module):
         plan.keep += [g1, b1, g2, b2]
         n, h, w = x.n, x.h, x.w
         xn = plan.buf(n, h, w, C)
-        plan.add(name + ".ln1", lambda s: L.E.layernorm(x, g1, b1, xn, self.norm1.eps, s), "layernorm", 0.0, 4.0 * n * h * w * C)
+        plan.add(name + ".ln1", lambda s: L.E.layernorm(x, g1, b1, xn, self.norm1.eps, s), "layernorm", 0.0, 4.0 * n * h * w * C,
+                 outs=[dict(view=xn, label=L.ref(self, ".ln1"))])
         qkv = plan.buf(n, h, w, 3 * C)
-        plan.conv(name + ".qkv", xn, PackedConv(self.self_attn.in_proj_weight, self.self_attn.in_proj_bias, dev), qkv, 1, ACT_NONE)
+        plan.conv(name + ".qkv", xn, PackedConv(self.self_attn.in_proj_weight, self.self_attn.in_proj_bias, dev), qkv, 1, ACT_NONE,
+                  label=L.ref(self, ".qkv"))
         o = plan.buf(n, h, w, C)
         scale = 1.0 / math.sqrt(C // self.num_heads)
         ntok = h * w
         plan.add(name + ".attn", lambda s: L.E.flash_attn(qkv, o, self.num_heads, scale, s), "attention",
-                 4.0 * n * float(ntok) * ntok * C, 2.0 * n * ntok * 4 * C)  # 4*N^2*C per image
+                 4.0 * n * float(ntok) * ntok * C, 2.0 * n * ntok * 4 * C,  # 4*N^2*C per image
+                 outs=[dict(view=o, label=L.ref(self, ".attn"))])
         t = plan.buf(n, h, w, C)
-        plan.conv(name + ".proj", o, PackedConv(self.self_attn.out_proj.weight, self.self_attn.out_proj.bias, dev), t, 1, ACT_NONE, x)
+        plan.conv(name + ".proj", o, PackedConv(self.self_attn.out_proj.weight, self.self_attn.out_proj.bias, dev), t, 1, ACT_NONE, x,
+                  label=L.ref(self, ".proj"))
         xn2 = plan.buf(n, h, w, C)
-        plan.add(name + ".ln2", lambda s: L.E.layernorm(t, g2, b2, xn2, self.norm2.eps, s), "layernorm", 0.0, 4.0 * n * h * w * C)
+        plan.add(name + ".ln2", lambda s: L.E.layernorm(t, g2, b2, xn2, self.norm2.eps, s), "layernorm", 0.0, 4.0 * n * h * w * C,
+                 outs=[dict(view=xn2, label=L.ref(self, ".ln2"))])
         ff0, ff3 = self.feedforward[0], self.feedforward[3]
         hid = plan.buf(n, h, w, ff0.out_features)
-        plan.conv(name + ".ff0", xn2, PackedConv(ff0.weight, ff0.bias, dev), hid, 1, ACT_RELU)
+        plan.conv(name + ".ff0", xn2, PackedConv(ff0.weight, ff0.bias, dev), hid, 1, ACT_RELU, label=L.ref(self, ".ff0"))
         if out is None:
             out = plan.buf(n, h, w, C)
-        return plan.conv(name + ".ff3", hid, PackedConv(ff3.weight, ff3.bias, dev), out, 1, ACT_NONE, t)
+        return plan.conv(name + ".ff3", hid, PackedConv(ff3.weight, ff3.bias, dev), out, 1, ACT_NONE, t, label=L.ref(self, ".ff3"))
 
     def forward(self, x):
         return L.run_module(self, x)

@@ -35,7 +35,7 @@ class ConvolutionBlock(nn.Module):
         if out is None:
             up = 2 if upsample2x else 1
             out = plan.buf(x.n, x.h // s * up, x.w // s * up, self.out_channels)
-        return plan.conv(name, x, self.packed(plan.device, x.c), out, s, ACT_SILU, residual, upsample2x)
+        return plan.conv(name, x, self.packed(plan.device, x.c), out, s, ACT_SILU, residual, upsample2x, label=L.ref(self))
 
     def forward(self, x):
         return L.run_module(self, x)
@@ -77,7 +77,7 @@ class CSPBlock(nn.Module):
         cat = plan.buf(x.n, x.h, x.w, 2 * h)
         # cv1 and cv2 read the same input: one GEMM with N = 2*hidden writes both halves of the concat
         fused = PackedConv.concat([self.cv1.packed(plan.device, x.c), self.cv2.packed(plan.device, x.c)])
-        plan.conv(name + ".cv1|cv2", x, fused, cat, 1, ACT_SILU)
+        plan.conv(name + ".cv1|cv2", x, fused, cat, 1, ACT_SILU, label=[(0, h, L.ref(self.cv1)), (h, 2 * h, L.ref(self.cv2))])
         y = cat.slice(0, h)
         for i, b in enumerate(self.bottlenecks):
             b.lower(plan, y, name=f"{name}.m{i}")
@@ -105,7 +105,8 @@ class SPPBlock(nn.Module):
         self.cv1.lower(plan, x, cat.slice(0, h), name=name + ".cv1")
         for i in range(3):  # mp9 = mp5(mp5), mp13 = mp5(mp5(mp5)) with -inf padding: exact
             src, dst = cat.slice(i * h, (i + 1) * h), cat.slice((i + 1) * h, (i + 2) * h)
-            plan.add(f"{name}.mp{5 + 4 * i}", lambda s, a=src, b=dst: L.E.maxpool5(a, b, s), "maxpool", 0.0, 4.0 * x.n * x.h * x.w * h)
+            plan.add(f"{name}.mp{5 + 4 * i}", lambda s, a=src, b=dst: L.E.maxpool5(a, b, s), "maxpool", 0.0, 4.0 * x.n * x.h * x.w * h,
+                     outs=[dict(view=dst, label=L.ref(self, f".mp{5 + 4 * i}"))])
         return self.cv2.lower(plan, cat, out, name=name + ".cv2")
 
     def forward(self, x):
@@ -135,5 +136,6 @@ class FocusBlock(nn.Module):
         ho, wo = h // 2, w // 2
         flops = 2.0 * n * ho * wo * c.out_channels * 9 * 12
         nbytes = 3.0 * n * h * w + 2.0 * (2.0 * n * ho * (wo + 4) * 16) + 2.0 * n * ho * wo * c.out_channels  # uint8 image
-        plan.add(name, lambda s: L.E.focus_conv(img_holder[0], pw, out, ws, ACT_SILU, s), "conv", flops, nbytes, 2)
+        plan.add(name, lambda s: L.E.focus_conv(img_holder[0], pw, out, ws, ACT_SILU, s), "conv", flops, nbytes, 2,
+                 outs=[dict(view=out, label=L.ref(c))])
         return out

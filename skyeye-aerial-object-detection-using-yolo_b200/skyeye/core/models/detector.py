@@ -18,6 +18,7 @@ import torch.nn as nn
 import yaml
 
 from ... import engine as E
+from .. import _lowering as L
 from ...engine import ACT_NONE, PackedConv, Plan, View
 from .attention import CrossLayerAttention, TransformerLayer
 from .backbone import SkyEyeBackbone
@@ -52,14 +53,16 @@ class DetectionHead(nn.Module):
         raws = []
         for i, (f, layer) in enumerate(zip(feats, self.detection_layers)):
             r = plan.buf(f.n, f.h, f.w, cpad, torch.float32)
-            plan.conv(f"head.{i}", f, PackedConv(layer.weight, layer.bias, plan.device), r, 1, ACT_NONE)
+            plan.conv(f"head.{i}", f, PackedConv(layer.weight, layer.bias, plan.device), r, 1, ACT_NONE, label=L.ref(layer))
             raws.append(r)
         rows = sum(na * r.h * r.w for r in raws)
         det = torch.empty((raws[0].n, rows, no), dtype=torch.float32, device=plan.device)
         raw_out = [torch.empty((r.n, na, r.h, r.w, no), dtype=torch.float32, device=plan.device) for r in raws]
         plan.keep += [det, raw_out]
         plan.add("decode", lambda s: E.decode(raws, na, no, self.anchors, input_hw, det, raw_out, s), "decode", 0.0,
-                 4.0 * raws[0].n * rows * no * 3)
+                 4.0 * raws[0].n * rows * no * 3,
+                 outs=[dict(view=det, label="det" if L.ref(self) else None, layout="flat")] +
+                      [dict(view=t, label=L.ref(layer), layout="raw", na=na) for t, layer in zip(raw_out, self.detection_layers)])
         return det, raw_out
 
 
@@ -226,6 +229,8 @@ class SkyEyeDetector(nn.Module):
         if h % 32 or w % 32:
             raise ValueError(f"input H, W must be multiples of 32 (got {h}x{w}); letterbox first")
         plan = Plan(device)
+        for name, m in self.named_modules():  # reference state-dict paths label the plan's outputs (Plan.run_teacher_forced)
+            m._ref = name
         feats = self._lower_features(plan, n, h, w)
         plan.det, plan.raw_out = self.detection_head.lower(plan, feats, (h, w))
         plan.feats = feats

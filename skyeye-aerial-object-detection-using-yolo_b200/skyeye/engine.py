@@ -222,6 +222,7 @@ class Plan:
         self.steps: List[Callable[[int], None]] = []
         self.names: List[str] = []
         self.meta: List[dict] = []  # per step: kind, algorithmic flops / bytes, kernel launches
+        self.outs: List[list] = []  # per step: what it writes, labelled with the reference module path (teacher forcing)
         self.keep = []  # buffers / packed weights kept alive
         self.graph = None
         self.n_launch_calls = 0
@@ -237,21 +238,30 @@ class Plan:
         return t
 
     def add(self, name: str, fn: Callable[[int], None], kind: str = "other", flops: float = 0.0, bytes: float = 0.0,
-            launches: int = 1) -> None:
+            launches: int = 1, outs: Optional[list] = None) -> None:
+        """``outs``: [dict(view=View | Tensor, label=<reference state-dict path of the producing module>,
+        layout='nhwc' | 'raw' | 'flat', up2=bool, na=int)] -- consumed by ``run_teacher_forced``."""
         self.names.append(name)
         self.steps.append(fn)
         self.meta.append(dict(kind=kind, flops=float(flops), bytes=float(bytes), launches=int(launches)))
+        self.outs.append([o for o in (outs or []) if o.get("label")])
 
     # -- op builders ---------------------------------------------------------------------------
-    def conv(self, name, x: View, pw: PackedConv, y: View, stride=1, act=ACT_SILU, residual=None, upsample2x=False):
+    def conv(self, name, x: View, pw: PackedConv, y: View, stride=1, act=ACT_SILU, residual=None, upsample2x=False, label=None):
+        """``label``: reference module path of the output, or [(c0, c1, path)] for a fused GEMM writing several
+        modules' outputs into channel slices of ``y``."""
         self.keep.append(pw)
+        if isinstance(label, str):
+            outs = [dict(view=y.slice(0, min(pw.cout, y.c)), label=label, up2=upsample2x)]
+        else:
+            outs = [dict(view=y.slice(c0, c1), label=lb, up2=upsample2x) for c0, c1, lb in (label or [])]
         ho, wo = x.h // stride, x.w // stride
         m = x.n * ho * wo
         flops = 2.0 * m * pw.cout * pw.k * pw.k * pw.cin_real  # algorithmic 2*M*N*K (SURVEY.md §8d), unpadded
         esz = 4 if y.dtype == SKB_F32 else 2
         nbytes = 2.0 * x.n * x.h * x.w * x.c + 2.0 * pw.w.numel() + esz * m * y.c * (4 if upsample2x else 1) + \
             (2.0 * m * y.c if residual is not None else 0.0)
-        self.add(name, lambda s: conv2d(x, pw, y, stride, act, residual, upsample2x, s), "conv", flops, nbytes, 1)
+        self.add(name, lambda s: conv2d(x, pw, y, stride, act, residual, upsample2x, s), "conv", flops, nbytes, 1, outs)
         return y
 
     def run(self, stream: Optional[int] = None) -> None:
@@ -275,6 +285,48 @@ class Plan:
             evs.append((a, b))
         torch.cuda.synchronize()
         return [(n, a.elapsed_time(b)) for n, (a, b) in zip(self.names, evs)]
+
+    @staticmethod
+    def _expected(o: dict, taps: dict) -> torch.Tensor:
+        t = taps[o["label"]]
+        layout = o.get("layout", "nhwc")
+        if layout == "flat":
+            return t
+        if layout == "raw":  # DetectionHead.forward's view + permute (detector.py:81-82)
+            b, c, h, w = t.shape
+            na = o["na"]
+            return t.view(b, na, c // na, h, w).permute(0, 1, 3, 4, 2)
+        if o.get("up2"):  # nearest 2x upsample fused into the producer's stores (detector.py:214,218)
+            t = t.repeat_interleave(2, 2).repeat_interleave(2, 3)
+        return t.permute(0, 2, 3, 1)
+
+    def run_teacher_forced(self, taps: dict) -> List[dict]:
+        """Verification mode: run the launches one by one; after each, compare what it wrote with ``taps[label]``
+        (NCHW fp32 host tensors keyed by reference module path, produced by an external reference run on the same
+        input and weights) and then OVERWRITE the output with the reference values, so every launch reads exactly
+        the reference's input for it.  Per-launch errors therefore do not chain.  Returns one row per output."""
+        rows = []
+        s = _stream_ptr()
+        for name, fn, outs, meta in zip(self.names, self.steps, self.outs, self.meta):
+            fn(s)
+            torch.cuda.synchronize()
+            for o in outs:
+                got = o["view"].torch() if isinstance(o["view"], View) else o["view"]
+                exp = self._expected(o, taps).to(got.device, torch.float32)
+                assert tuple(got.shape) == tuple(exp.shape), (name, o["label"], tuple(got.shape), tuple(exp.shape))
+                d = (got.float() - exp).abs()
+                if got.dtype == torch.bfloat16:
+                    # what is left after allowing the stored value to land on the neighbouring bf16 number (a 1e-7 difference
+                    # in the fp32 result flips the rounding of a value that sits on a rounding boundary)
+                    ulp = torch.exp2(torch.floor(torch.log2(exp.abs().clamp_min(1e-30))) - 7.0)
+                    beyond = float((d - ulp).clamp_min(0).max())
+                else:
+                    beyond = float(d.max())
+                rows.append(dict(step=name, label=o["label"], kind=meta["kind"], store="f32" if got.dtype == torch.float32 else "bf16",
+                                 max_err=float(d.max()), beyond_ulp=beyond, rms_err=float(d.pow(2).mean().sqrt()),
+                                 ref_max=float(exp.abs().max()), ref_rms=float(exp.pow(2).mean().sqrt()), numel=exp.numel()))
+                got.copy_(exp)
+        return rows
 
     def capture(self) -> None:
         """Capture the whole plan into a CUDA graph (tensor maps are baked in as kernel params)."""
