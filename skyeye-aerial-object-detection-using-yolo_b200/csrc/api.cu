@@ -18,17 +18,35 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-static int g_dev_checked = 0;  // 0 unknown, 1 ok, -1 bad arch
-static int g_num_sms = 0;
+constexpr int MAX_DEV = 64;
+static int g_dev_checked[MAX_DEV];  // per device ordinal: 0 unknown, 1 ok
+static int g_num_sms[MAX_DEV];
+static std::mutex g_dev_mu;
+
+bool PerDeviceOnce::first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return true;  // cannot tell: redo the (idempotent) action
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    const unsigned long long bit = 1ULL << dev;
+    if (seen & bit) return false;
+    seen |= bit;
+    return true;
+}
+void PerDeviceOnce::reset_current() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return;
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    seen &= ~(1ULL << dev);
+}
 
 int check_device() {
-    if (g_dev_checked == 1) return SKB_OK;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) {
         set_error("no CUDA device: %s", cudaGetErrorString(e));
         return SKB_ERR_CUDA;
     }
+    if (dev >= 0 && dev < MAX_DEV && g_dev_checked[dev] == 1) return SKB_OK;
     cudaDeviceProp prop;
     e = cudaGetDeviceProperties(&prop, dev);
     if (e != cudaSuccess) {
@@ -40,12 +58,19 @@ int check_device() {
                   prop.major, prop.minor, prop.name);
         return SKB_ERR_ARCH;
     }
-    g_num_sms = prop.multiProcessorCount;
-    g_dev_checked = 1;
+    if (dev >= 0 && dev < MAX_DEV) {
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        g_num_sms[dev] = prop.multiProcessorCount;
+        g_dev_checked[dev] = 1;
+    }
     return SKB_OK;
 }
 
-int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+int num_sms() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return 148;
+    return g_num_sms[dev] > 0 ? g_num_sms[dev] : 148;
+}
 
 int pdl_enabled() {  // tuning knob (not part of the ABI): SKB_PDL=0 launches every kernel fully serialised
     static int v = -1;

@@ -119,7 +119,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     auto s_full = [&](int g, int s) { return bar0 + 8u * (2 * NQ + 2 * KVS + 2 * g + s); };
     auto p_full = [&](int g, int s) { return bar0 + 8u * (4 * NQ + 2 * KVS + 2 * g + s); };
     auto o_done = [&](int g) { return bar0 + 8u * (6 * NQ + 2 * KVS + g); };
-    const uint32_t slot = bar0 + 8u * (7 * NQ + 2 * KVS);
+    // Completion of the LAST PV MMA only.  The epilogue must not wait on o_done: a softmax warp can reach the epilogue while
+    // PV(T-2) is still waiting for a slower warp's P (one that took the rescale path late in the sequence); o_done is then two
+    // phases behind and a parity wait for phase T-1 falls straight through (parity aliasing) -> O read before the last two
+    // tiles were accumulated.  Found by the teacher-forced parity test on real activations (keys peaking in the last tile).
+    auto o_final = [&](int g) { return bar0 + 8u * (7 * NQ + 2 * KVS + g); };
+    const uint32_t slot = bar0 + 8u * (8 * NQ + 2 * KVS);
     volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -136,6 +141,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 mbar_init(q_full(g), 1);
                 mbar_init(q_ready(g), 4);
                 mbar_init(o_done(g), 1);
+                mbar_init(o_final(g), 1);
                 for (int s = 0; s < 2; ++s) { mbar_init(s_full(g, s), 1); mbar_init(p_full(g, s), 4); }
             }
             for (int s = 0; s < KVS; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), NQ); }
@@ -224,6 +230,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     umma_bf16_ts(tmem_O, tmem + sb * ATT_BKV + k * 8, bd + (uint64_t)(k * 128), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
                 umma_commit(kv_empty(s));
                 umma_commit(o_done(g));
+                if (j == T - 1) umma_commit(o_final(g));
             }
             __syncwarp();
             if (PROF) { pf_m[0] += c1 - c0; pf_m[1] += clock64() - c1; }
@@ -366,7 +373,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             atomicAdd(&g_att_prof[13], (unsigned long long)pf_hop);
         }
         // ---- epilogue: O / l -> bf16 ----
-        mbar_wait(o_done(g), (uint32_t)(T - 1) & 1u);
+        mbar_wait(o_final(g), 0);
         tc_fence_after();
         const uint32_t lsum = tmem_ld1(tmem_L + lane_addr);
         tmem_ld_wait();
@@ -427,23 +434,27 @@ extern "C" int skb_flash_attn_bf16(const skb_view* qkv, const skb_view* o, int32
     static int poly = -1, nq_force = 0;
     if (poly < 0) {  // tuning knobs (not part of the ABI): SKB_ATT_POLY in {0, 8, 16}, SKB_ATT_NQ in {1, 2}
         const char* e = getenv("SKB_ATT_POLY");
-        poly = e ? atoi(e) : ATT_POLY_DEFAULT;
-        if (poly != 0 && poly != 8 && poly != 16) poly = ATT_POLY_DEFAULT;
+        int pv = e ? atoi(e) : ATT_POLY_DEFAULT;
+        if (pv != 0 && pv != 8 && pv != 16) pv = ATT_POLY_DEFAULT;
         e = getenv("SKB_ATT_NQ");
         nq_force = e ? atoi(e) : 0;
+        poly = pv;
+    }
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {  // the shared-memory opt-in is a per-device function attribute
         SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
         SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
         SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
         SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2>::SMEM));
         SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2>::SMEM));
         SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2>::SMEM));
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2>::SMEM));
     }
     static int prof = -1;
     if (prof < 0) {
         const char* e = getenv("SKB_ATT_PROF");
         prof = e ? atoi(e) : 0;
-        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
-        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2>::SMEM));
     }
     // two query tiles per CTA once the K/V stream is long enough to matter (and 256-row tiles waste little of N)
     const int nq = nq_force == 1 || nq_force == 2 ? nq_force : (N >= 4096 ? 2 : 1);

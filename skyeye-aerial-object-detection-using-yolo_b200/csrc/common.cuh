@@ -45,6 +45,13 @@ int check_device();  // SKB_OK or SKB_ERR_ARCH / SKB_ERR_CUDA (message set)
     } while (0)
 
 int num_sms();
+// Function attributes (the dynamic shared-memory opt-in) and the architecture check are PER DEVICE: every call site owns one
+// of these and asks `first()` with the current device; true exactly once per device, thread-safe.
+struct PerDeviceOnce {
+    unsigned long long seen = 0ULL;  // bit d = done on CUDA device d (d < 64)
+    bool first();
+    void reset_current();             // undo (the guarded action failed)
+};
 // launch attribute list for kernels that call pdl_wait(): programmatic stream serialization (PDL)
 int pdl_enabled();
 

@@ -752,11 +752,9 @@ template <int BN>
 static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR, const HaloParams& p,
                        cudaStream_t stream) {
     using Cfg = HaloCfg<BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first())
         SKB_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
     const int grid = p.total_items < num_sms() ? p.total_items : num_sms();
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -783,11 +781,9 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     const CUtensorMap& u1 = tmU ? tmU[0] : tmY;
     const CUtensorMap& u2 = tmU ? tmU[1] : tmY;
     const CUtensorMap& u3 = tmU ? tmU[2] : tmY;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first())
         SKB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BK, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
     const int units = num_sms() / NCTA;  // CTAs (or CTA pairs) resident at once
     const int grid = (p.total_tiles < units ? p.total_tiles : units) * NCTA;
     cudaLaunchConfig_t cfg;

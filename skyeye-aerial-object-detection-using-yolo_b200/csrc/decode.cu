@@ -5,9 +5,10 @@
 
 namespace skb {
 
-constexpr int DEC_PIX = 64;       // pixels per CTA chunk
+constexpr int DEC_PIX = 64;       // pixels per CTA chunk (32 when a pixel carries more than 128 head channels)
 constexpr int DEC_THREADS = 256;
-constexpr int DEC_MAX_CH = 8 * 16;  // na * no staged per pixel (<= 128 floats)
+constexpr int DEC_MAX_CH = 256;   // na * no staged per pixel: 3 * 85 = 255 for the reference default num_classes = 80 (detector.py:28)
+constexpr int DEC_SMEM_FLOATS = 64 * 128;
 
 struct DecodeLevel {
     const float* raw;   // [B, h, w, pitch] fp32, channel = a*no + o
@@ -23,6 +24,7 @@ struct DecodeLevel {
 struct DecodeParams {
     DecodeLevel lv[4];
     int levels, na, no, B;
+    int pix;            // pixels per CTA: pix * 4 * ceil(na*no / 4) <= DEC_SMEM_FLOATS
     unsigned int no_magic;  // ceil(2^20 / no): i / no == (i * no_magic) >> 20 for every i < DEC_PIX * no (checked on the host)
     long rows_per_image;
 };
@@ -39,7 +41,7 @@ __device__ __forceinline__ float sigmoid_acc(float x) { return __frcp_rn(1.0f + 
 // records: 0.94 TB/s.)
 __global__ void __launch_bounds__(DEC_THREADS)
 decode_kernel(const DecodeParams p, float* __restrict__ det) {
-    __shared__ __align__(16) float sin_[DEC_PIX * DEC_MAX_CH];
+    __shared__ __align__(16) float sin_[DEC_SMEM_FLOATS];
     __shared__ float sgx[DEC_PIX], sgy[DEC_PIX];  // grid (x, y) of the chunk's pixels
     int l = 0;
     while (l + 1 < p.levels && (int)blockIdx.x >= p.lv[l + 1].chunk0) ++l;
@@ -47,8 +49,8 @@ decode_kernel(const DecodeParams p, float* __restrict__ det) {
     const int cb = (int)blockIdx.x - L.chunk0;
     const int b = cb / L.chunks_per_image;
     const int hw = L.h * L.w;
-    const int pix0 = (cb - b * L.chunks_per_image) * DEC_PIX;
-    const int npix = min(DEC_PIX, hw - pix0);
+    const int pix0 = (cb - b * L.chunks_per_image) * p.pix;
+    const int npix = min(p.pix, hw - pix0);
     const int nch = p.na * p.no;
     const int nch4 = (nch + 3) >> 2;  // 16-byte vectors per pixel (host guarantees pitch >= 4*nch4)
     const float* src = L.raw + ((long)b * hw + pix0) * L.pitch;
@@ -106,6 +108,7 @@ extern "C" int skb_decode_f32(const skb_view* raw, int32_t levels, int32_t na, i
     DecodeParams p;
     memset(&p, 0, sizeof(p));
     p.levels = levels; p.na = na; p.no = no; p.B = raw[0].n;
+    p.pix = (na * no + 3) / 4 * 4 <= 128 ? DEC_PIX : DEC_PIX / 2;
     p.no_magic = ((1u << 20) + (unsigned int)no - 1u) / (unsigned int)no;
     for (unsigned int i = 0; i < (unsigned int)(DEC_PIX * no); ++i)
         SKB_REQUIRE(((i * p.no_magic) >> 20) == i / (unsigned int)no, SKB_ERR_UNSUPPORTED, "decode: no=%d outside the fast-division range", no);
@@ -125,7 +128,7 @@ extern "C" int skb_decode_f32(const skb_view* raw, int32_t levels, int32_t na, i
         for (int a = 0; a < na; ++a)
             for (int k = 0; k < 2; ++k) L.anchor[a][k] = anchors_host[(l * na + a) * 2 + k] * L.stride;
         row += (long)na * v.h * v.w;
-        L.chunks_per_image = (v.h * v.w + DEC_PIX - 1) / DEC_PIX;
+        L.chunks_per_image = (v.h * v.w + p.pix - 1) / p.pix;
         L.chunk0 = chunk;
         chunk += L.chunks_per_image * p.B;
     }

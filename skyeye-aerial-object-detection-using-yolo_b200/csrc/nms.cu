@@ -110,8 +110,9 @@ static size_t nms_layout(int n, void* base, NmsWs* ws) {
 // =============================================================================================
 // (2) batched wrapper
 // =============================================================================================
-constexpr int KEY_SLOT_BITS = 22;
-constexpr int KEY_IMG_BITS = 10;
+// sort key = [image | ~score (32 bits) | slot]: the slot field is sized per call for N * nc (nc = 80 at 1280^2 needs 23 bits),
+// the image field takes what is left of the upper 32 bits
+constexpr int KEY_MAX_SLOT_BITS = 27;
 constexpr int MAX_NMS_BOXES = 30000;  // metrics.py:393
 constexpr int NMS_THREADS = 512;
 constexpr int NMS_MAX_KEEP = 1024;
@@ -121,6 +122,7 @@ struct FilterParams {
     int B, N, nc, no;
     float conf;
     int multi_label, compat;
+    int slot_bits;
     int n_classes;
     float classes[32];
 };
@@ -156,7 +158,7 @@ __global__ void nms_filter_kernel(const FilterParams p, unsigned long long* __re
             unsigned long long* kout = keys + i * per;
             const bool pass = obj > p.conf;  // metrics.py:391,402
             auto key_of = [&](float score, int slot) {
-                return ((unsigned long long)b << (32 + KEY_SLOT_BITS)) | ((unsigned long long)desc_bits(score) << KEY_SLOT_BITS) |
+                return ((unsigned long long)b << (32 + p.slot_bits)) | ((unsigned long long)desc_bits(score) << p.slot_bits) |
                        (unsigned long long)slot;
             };
             const unsigned long long none = ~0ULL;
@@ -210,6 +212,7 @@ struct BatchedParams {
     float iou;
     int agnostic, multi_label, compat, max_det;
     int capacity;
+    int slot_bits;
 };
 
 struct Cand {
@@ -218,7 +221,7 @@ struct Cand {
 };
 
 __device__ __forceinline__ void load_cand(const BatchedParams& p, int b, unsigned long long key, Cand& c) {
-    const int slot = (int)(key & ((1ULL << KEY_SLOT_BITS) - 1));
+    const int slot = (int)(key & ((1ULL << p.slot_bits) - 1));
     int r, j;
     const bool per_class = p.nc > 1 || (p.compat == 1 && p.nc == 1);
     if (per_class) { r = slot / p.nc; j = slot - r * p.nc; } else { r = slot; j = 0; }
@@ -407,8 +410,12 @@ extern "C" int skb_nms_batched_f32(const float* pred, int32_t b, int32_t n, int3
     SKB_REQUIRE(pred && out && out_count && workspace && b > 0 && n > 0 && nc >= 0, SKB_ERR_ARG, "nms_batched: bad arguments");
     SKB_REQUIRE(compat == 0 || compat == 1, SKB_ERR_ARG, "nms_batched: compat must be 0 (reference) or 1 (fixed)");
     SKB_REQUIRE(max_det >= 1 && max_det <= NMS_MAX_KEEP, SKB_ERR_UNSUPPORTED, "nms_batched: max_det=%d (supported: 1..%d)", max_det, NMS_MAX_KEEP);
-    SKB_REQUIRE(b <= (1 << KEY_IMG_BITS) && (long)n * (nc > 1 ? nc : 1) <= (1L << KEY_SLOT_BITS), SKB_ERR_UNSUPPORTED,
-                "nms_batched: B=%d N*nc=%ld exceed the sort-key fields", b, (long)n * (nc > 1 ? nc : 1));
+    int slot_bits = 1, img_bits = 1;
+    while ((1L << slot_bits) < (long)n * (nc > 1 ? nc : 1)) ++slot_bits;
+    while ((1 << img_bits) < b) ++img_bits;
+    SKB_REQUIRE(slot_bits <= KEY_MAX_SLOT_BITS && slot_bits + img_bits <= 32, SKB_ERR_UNSUPPORTED,
+                "nms_batched: B=%d N*nc=%ld exceed the 64-bit sort key (image %d + slot %d bits > 32)", b, (long)n * (nc > 1 ? nc : 1),
+                img_bits, slot_bits);
     SKB_REQUIRE(n_classes <= 32, SKB_ERR_UNSUPPORTED, "nms_batched: at most 32 class filters");
     multi_label = (multi_label && nc > 1) ? 1 : 0;  // metrics.py:396
     SKB_REQUIRE(workspace_bytes >= skb_nms_batched_workspace_bytes(b, n, nc, multi_label), SKB_ERR_WORKSPACE, "nms_batched: workspace too small");
@@ -420,6 +427,7 @@ extern "C" int skb_nms_batched_f32(const float* pred, int32_t b, int32_t n, int3
     FilterParams fp;
     memset(&fp, 0, sizeof(fp));
     fp.pred = pred; fp.B = b; fp.N = n; fp.nc = nc; fp.no = nc + 5; fp.conf = conf_thr; fp.multi_label = multi_label; fp.compat = compat;
+    fp.slot_bits = slot_bits;
     fp.n_classes = classes_host ? n_classes : 0;
     for (int i = 0; i < fp.n_classes; ++i) fp.classes[i] = (float)classes_host[i];
     const long nbox = (long)b * n;
@@ -427,18 +435,13 @@ extern "C" int skb_nms_batched_f32(const float* pred, int32_t b, int32_t n, int3
     const long gcap = (long)num_sms() * 16;
     nms_filter_kernel<<<(int)(g > gcap ? gcap : g), 256, 0, st>>>(fp, ws.keys_in, ws.count);
     SKB_LAUNCH_CHECK();
-    int img_bits = 1;
-    while ((1 << img_bits) < b) ++img_bits;
-    SKB_CUDA(cub::DeviceRadixSort::SortKeys(ws.cub_tmp, ws.cub_bytes, ws.keys_in, ws.keys_out, (long)cap, 0, 32 + KEY_SLOT_BITS + img_bits, st));
+    SKB_CUDA(cub::DeviceRadixSort::SortKeys(ws.cub_tmp, ws.cub_bytes, ws.keys_in, ws.keys_out, (long)cap, 0, 32 + slot_bits + img_bits, st));
     BatchedParams bp;
     bp.pred = pred; bp.B = b; bp.N = n; bp.nc = nc; bp.no = nc + 5; bp.iou = iou_thr; bp.agnostic = agnostic; bp.multi_label = multi_label;
-    bp.compat = compat; bp.max_det = max_det; bp.capacity = (int)cap;
+    bp.compat = compat; bp.max_det = max_det; bp.capacity = (int)cap; bp.slot_bits = slot_bits;
     constexpr int kMaskBytes = NMS_THREADS * (NMS_THREADS / 32) * (int)sizeof(unsigned int);
-    static bool attr_set = false;
-    if (!attr_set) {
-        SKB_CUDA(cudaFuncSetAttribute(nms_keptlist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaskBytes));
-        attr_set = true;
-    }
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) SKB_CUDA(cudaFuncSetAttribute(nms_keptlist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaskBytes));
     nms_keptlist_kernel<<<b, NMS_THREADS, kMaskBytes, st>>>(bp, ws.keys_out, ws.count, out, out_count);
     SKB_LAUNCH_CHECK();
     return SKB_OK;

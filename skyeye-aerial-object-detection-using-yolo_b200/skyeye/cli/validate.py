@@ -64,7 +64,13 @@ def save_one_json(pred, jdict, path, class_map):
     box = xyxy2xywh(pred[:, :4])
     box[:, :2] -= box[:, 2:] / 2
     for p, b in zip(pred.tolist(), box.tolist()):
-        jdict.append({"image_id": image_id, "category_id": int(p[5]), "bbox": [round(x, 3) for x in b], "score": round(p[4], 5)})
+        cid = int(p[5])
+        if class_map is not None:  # validate.py:63: class_map[int(p[5])] (dict or list; identity when the id is not mapped)
+            try:
+                cid = class_map[cid]
+            except (KeyError, IndexError):
+                pass
+        jdict.append({"image_id": image_id, "category_id": cid, "bbox": [round(x, 3) for x in b], "score": round(p[4], 5)})
 
 
 def process_batch(detections, labels, iouv):
@@ -126,10 +132,10 @@ class FolderLoader:
                 if lp.exists():
                     lab = np.loadtxt(lp, ndmin=2, dtype=np.float32).reshape(-1, 5)
                     if lab.size:
-                        # normalised original-image xywh -> normalised letterboxed-image xywh
-                        cx = (lab[:, 1] * w0 * r + pw) / im.shape[1]
-                        cy = (lab[:, 2] * h0 * r + ph) / im.shape[0]
-                        bw, bh = lab[:, 3] * w0 * r / im.shape[1], lab[:, 4] * h0 * r / im.shape[0]
+                        # normalised original-image xywh -> PIXELS of the letterboxed image (which sits at the top-left of the
+                        # batch frame); normalised by the batch frame below, once its size is known
+                        cx, cy = lab[:, 1] * w0 * r + pw, lab[:, 2] * h0 * r + ph
+                        bw, bh = lab[:, 3] * w0 * r, lab[:, 4] * h0 * r
                         tg.append(np.stack([np.full(len(lab), k, np.float32), lab[:, 0], cx, cy, bw, bh], 1))
                 paths.append(str(f))
                 shapes.append(((h0, w0), ((r, r), (pw, ph))))
@@ -139,6 +145,9 @@ class FolderLoader:
                 batch[k, :a.shape[0], :a.shape[1]] = a
             img = torch.from_numpy(np.ascontiguousarray(batch[..., ::-1].transpose(0, 3, 1, 2)))  # BGR -> RGB, NCHW
             targets = torch.from_numpy(np.concatenate(tg, 0)) if tg else torch.zeros((0, 6))
+            # images of different aspect ratios letterbox to different sizes; validate() rescales targets by the BATCH frame
+            # (validate.py:252), so that is what they are normalised by
+            targets[:, 2:] /= torch.tensor([W, H, W, H], dtype=targets.dtype)
             yield img, targets, paths, shapes
 
 
@@ -227,7 +236,7 @@ def validate(data, weights=None, batch_size=32, img_size=640, conf_thres=0.001, 
             if save_txt:
                 save_one_txt(predn.cpu(), save_conf, shape0, Path(save_dir) / "labels" / (Path(paths[si]).stem + ".txt"))
             if save_json:
-                save_one_json(predn.cpu(), jdict, paths[si], names)
+                save_one_json(predn.cpu(), jdict, paths[si], list(range(max(nc, 1))))
     nt = np.zeros(1)
     if stats:
         tp, conf, pcls, tcls_all = (np.concatenate(x, 0) for x in zip(*stats))

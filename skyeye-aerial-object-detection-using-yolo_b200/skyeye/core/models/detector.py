@@ -128,7 +128,9 @@ def _load_cfg(cfg) -> dict:
 
 
 class Results:
-    """Per-image detections of a README-style call ``model(image)`` (README.md:46-53)."""
+    """Per-image detections of a README-style call ``model(image)`` (README.md:46-53).  ``pred[i]`` holds rows
+    ``[x1, y1, x2, y2, conf, cls]`` in ORIGINAL-image pixels (rows of the reference wrapper's 7-column form
+    ``[cx, cy, w, h, obj, cls_prob, cls_id]`` are accepted too)."""
 
     def __init__(self, pred: List[torch.Tensor], images=None, names=None, files=None):
         self.pred, self.images, self.names = pred, images, names or []
@@ -137,19 +139,57 @@ class Results:
     def __len__(self):
         return len(self.pred)
 
+    @staticmethod
+    def _xyxy_conf_cls(p: torch.Tensor):
+        p = p.detach().float().cpu()
+        if p.shape[1] > 6:  # reference wrapper rows (quirk X8): centre form, class id in column 6
+            xy, wh = p[:, 0:2], p[:, 2:4]
+            return torch.cat((xy - wh / 2, xy + wh / 2), 1), p[:, 4], p[:, 6]
+        return p[:, :4], p[:, 4], p[:, 5]
+
+    def render(self) -> list:
+        """Annotated copies (BGR uint8) of the input images: box + ``name conf`` tag per detection."""
+        from ...utils.visualization import ImageAnnotator, colors
+        out = []
+        for im, p in zip(self.images or [], self.pred):
+            ann = ImageAnnotator(im.copy())
+            box, conf, cls = self._xyxy_conf_cls(p)
+            for b, c, k in zip(box.tolist(), conf.tolist(), cls.tolist()):
+                name = self.names[int(k)] if int(k) < len(self.names) else str(int(k))
+                ann.box_label(b, f"{name} {c:.2f}", color=colors(int(k)))
+            out.append(ann.result())
+        return out
+
     def save(self, save_dir="outputs/"):
-        """Writes one ``<name>.txt`` per image, rows ``cls cx cy w h conf`` in pixels."""
+        """Writes ``<name>.jpg`` (annotated image) and ``<name>.txt`` (rows ``cls x1 y1 x2 y2 conf`` in pixels) per image."""
+        import cv2
         os.makedirs(save_dir, exist_ok=True)
-        for f, p in zip(self.files, self.pred):
-            with open(os.path.join(save_dir, Path(f).stem + ".txt"), "w") as fh:
-                for row in p.tolist():
-                    cls = int(row[6]) if len(row) > 6 else int(row[5])
-                    fh.write(("%d " + "%g " * 5).rstrip() % (cls, *row[:4], row[4]) + "\n")
+        drawn = self.render()
+        for i, (f, p) in enumerate(zip(self.files, self.pred)):
+            stem = Path(f).stem
+            box, conf, cls = self._xyxy_conf_cls(p)
+            with open(os.path.join(save_dir, stem + ".txt"), "w") as fh:
+                for b, c, k in zip(box.tolist(), conf.tolist(), cls.tolist()):
+                    fh.write(("%d " + "%g " * 5).rstrip() % (int(k), *b, c) + "\n")
+            if i < len(drawn):
+                cv2.imwrite(os.path.join(save_dir, stem + ".jpg"), drawn[i])
         return save_dir
 
     def show(self):
+        """Prints a one-line summary per image and, when a display is available, opens the annotated images."""
         for f, p in zip(self.files, self.pred):
-            print(f"{f}: {p.shape[0]} detections")
+            _, _, cls = self._xyxy_conf_cls(p)
+            ids, cnt = (torch.unique(cls.long(), return_counts=True) if p.shape[0] else (torch.zeros(0), torch.zeros(0)))
+            parts = [f"{int(n)} {self.names[int(k)] if int(k) < len(self.names) else int(k)}" for k, n in zip(ids.tolist(), cnt.tolist())]
+            print(f"{f}: {p.shape[0]} detections" + (" (" + ", ".join(parts) + ")" if parts else ""))
+        if os.environ.get("DISPLAY") and self.images:
+            try:
+                import cv2
+                for f, im in zip(self.files, self.render()):
+                    cv2.imshow(str(f), im)
+                cv2.waitKey(1)
+            except Exception:
+                pass
         return self
 
 
@@ -176,8 +216,12 @@ class SkyEyeDetector(nn.Module):
         self.names = [str(i) for i in range(self.cfg["nc"])]
         self._plans = {}
         self._img = [None]
-        self.reuse_output_buffers = False
-        self.use_cuda_graph = False
+        # The forward plan is captured into a CUDA graph per input shape and replayed, and the returned tensors are the
+        # plan's own output buffers: they are valid until the next forward call with the same input shape.  Set
+        # reuse_output_buffers = False to get private copies (two device copies per call), use_cuda_graph = False to launch
+        # kernel by kernel.
+        self.reuse_output_buffers = True
+        self.use_cuda_graph = True
         self.eval()
         if weights is not None:
             self.load_from_pretrained(weights)
@@ -213,6 +257,15 @@ class SkyEyeDetector(nn.Module):
         ok = {k: v for k, v in sd.items() if k in own and v.shape == own[k].shape}
         self.load_state_dict(ok, strict=False)
         print(f"Loaded {len(ok)}/{len(own)} layers from {weights_path}")
+        # strict=False hides parameters the checkpoint did not provide (they keep their random init): say which
+        self.uninitialized_keys = [k for k in own if k not in ok and not k.endswith("num_batches_tracked")]
+        self.unexpected_keys = [k for k in sd if k not in ok]
+        if self.uninitialized_keys:
+            import warnings
+            mods = sorted({k.rsplit(".", 1)[0] for k in self.uninitialized_keys})
+            warnings.warn(f"{weights_path}: {len(self.uninitialized_keys)} parameters of {type(self).__name__} were NOT in the checkpoint "
+                          f"(or had another shape) and keep their random initialisation: {mods[:6]}{' ...' if len(mods) > 6 else ''}; "
+                          f"{len(self.unexpected_keys)} checkpoint entries were not used", stacklevel=2)
         return self
 
     def load_state_dict(self, state_dict, strict=True, **kw):
@@ -237,7 +290,7 @@ class SkyEyeDetector(nn.Module):
         return plan
 
     def plan_for(self, x: torch.Tensor) -> Plan:
-        key = (tuple(x.shape), x.device.index)
+        key = (tuple(x.shape), x.dtype, x.device.index)  # uint8 and fp32 images take different first kernels / graph inputs
         plan = self._plans.get(key)
         if plan is None:
             n, _, h, w = x.shape
@@ -256,30 +309,40 @@ class SkyEyeDetector(nn.Module):
             raise RuntimeError("SkyEyeDetector (B200) needs a CUDA tensor; there is no CPU fallback")
         # fp32 images in [0,1] as in the reference; uint8 images are scaled by 1/255 inside the first kernel
         xin = x if (x.dtype in (torch.float32, torch.uint8) and x.is_contiguous()) else x.float().contiguous()
-        plan = self.plan_for(xin)
-        if self.use_cuda_graph:
-            if plan.graph is None:
-                plan.static_in = xin.clone()
-                self._img[0] = plan.static_in
-                plan.capture()
-            plan.static_in.copy_(xin)
-            plan.replay()
-        else:
-            self._img[0] = xin
-            plan.run()
+        with torch.cuda.device(xin.device):  # native launches use the CURRENT device's stream and per-device function attributes
+            plan = self.plan_for(xin)
+            if self.use_cuda_graph:
+                if plan.graph is None:
+                    plan.static_in = xin.clone()
+                    self._img[0] = plan.static_in
+                    plan.capture()
+                plan.static_in.copy_(xin)
+                plan.replay()
+            else:
+                self._img[0] = xin
+                plan.run()
         if self.reuse_output_buffers:
             return plan.det, plan.raw_out
         return plan.det.clone(), [r.clone() for r in plan.raw_out]
 
     @torch.no_grad()
     def predict(self, source, img_size=640, conf_thres=0.25, iou_thres=0.45, max_det=300) -> Results:
-        """README-style call on image path(s) / HWC uint8 array(s): letterbox -> forward -> NMS."""
-        from ...utils.general import load_images_gpu
+        """README-style call on image path(s) / HWC BGR uint8 array(s): letterbox -> forward -> NMS -> boxes mapped back to
+        the original image.  Rows are ``[x1, y1, x2, y2, conf, cls]`` (what the reference wrapper's docstring promises,
+        metrics.py:383; its actual 7-column centre-form rows cannot be drawn)."""
+        from ...utils.general import letterbox_geometry, load_images_gpu, scale_boxes
         from ...utils.metrics import non_max_suppression
         dev = next(self.parameters()).device
         batch, files, origs = load_images_gpu(source, img_size, dev)  # letterbox + BGR->RGB + HWC->CHW on the GPU, uint8
         det, _ = self.forward(batch)
-        return Results(non_max_suppression(det, conf_thres, iou_thres, max_detections=max_det), origs, self.names, files)
+        rows = non_max_suppression(det, conf_thres, iou_thres, max_detections=max_det, compat="fixed")
+        out = []
+        for r, im in zip(rows, origs):
+            r = r.clone()
+            _, _, _, _, top, left, ratio = letterbox_geometry(im.shape[0], im.shape[1], img_size)
+            scale_boxes(batch.shape[2:], r[:, :4], im.shape[:2], ((ratio, ratio), (left, top)))
+            out.append(r)
+        return Results(out, origs, self.names, files)
 
 
 class EnhancedSkyEyeDetector(SkyEyeDetector):
@@ -291,7 +354,9 @@ class EnhancedSkyEyeDetector(SkyEyeDetector):
         c3, c4, c5 = self.neck.out_channels
         self.cross_attention_p5_p4 = CrossLayerAttention(c4, c5, region_size=2, heads=4)
         self.cross_attention_p4_p3 = CrossLayerAttention(c3, c4, region_size=2, heads=4)
-        if self.cfg.get("head", "transformer") == "transformer":
+        # default = the reference architecture (bare 1x1 heads, detector.py:436-501); the transformer heads of the skyeye_l
+        # variant are selected by "head: transformer" in the model config
+        if self.cfg.get("head", "conv") == "transformer":
             hd = self.cfg.get("head_dim", 64)
             self.head_transformers = nn.ModuleList(TransformerLayer(c, max(c // hd, 1)) for c in (c3, c4, c5))
         else:

@@ -35,8 +35,9 @@ def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torc
     keep = torch.empty(max(n, 1), dtype=torch.int64, device=boxes.device)
     cnt = torch.zeros(1, dtype=torch.int32, device=boxes.device)
     ws = _workspace(N.lib().skb_nms_workspace_bytes(n), boxes.device)
-    N.check(N.lib().skb_nms_f32(boxes.data_ptr(), scores.data_ptr(), n, float(iou_threshold), keep.data_ptr(), cnt.data_ptr(),
-                                ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), "skb_nms_f32")
+    with torch.cuda.device(boxes.device):
+        N.check(N.lib().skb_nms_f32(boxes.data_ptr(), scores.data_ptr(), n, float(iou_threshold), keep.data_ptr(), cnt.data_ptr(),
+                                    ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), "skb_nms_f32")
     return keep[: int(cnt.item())]
 
 
@@ -60,8 +61,9 @@ def batched_nms_padded(prediction: torch.Tensor, conf_threshold=0.25, iou_thresh
     if classes is not None:
         ncls = len(classes)
         cls_arr = (ctypes.c_int32 * ncls)(*[int(c) for c in classes])
-    N.check(N.lib().skb_nms_batched_f32(pred.data_ptr(), B, Nb, nc, float(conf_threshold), float(iou_threshold), cls_arr, ncls,
-                                        1 if agnostic else 0, ml, int(max_detections), 0 if compat == "reference" else 1,
-                                        out.data_ptr(), out_count.data_ptr(), ws.data_ptr(), ws.numel(),
-                                        torch.cuda.current_stream().cuda_stream), "skb_nms_batched_f32")
+    with torch.cuda.device(pred.device):
+        N.check(N.lib().skb_nms_batched_f32(pred.data_ptr(), B, Nb, nc, float(conf_threshold), float(iou_threshold), cls_arr, ncls,
+                                            1 if agnostic else 0, ml, int(max_detections), 0 if compat == "reference" else 1,
+                                            out.data_ptr(), out_count.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            torch.cuda.current_stream().cuda_stream), "skb_nms_batched_f32")
     return out, out_count

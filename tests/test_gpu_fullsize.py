@@ -77,7 +77,7 @@ def _build_l():
     from oracle import model as om
     from skyeye.core.detector import construct_model
     cfg = om.get_cfg("skyeye_l")
-    sd = om.make_state_dict(cfg, 0)
+    sd = om.make_calibrated_state_dict(cfg, 0)   # the benchmark's weights (activations O(1): attention / CLA see real logits)
     m = construct_model("skyeye_l.yaml")
     m.load_state_dict(sd, strict=True)
     return m.cuda().eval()

@@ -103,20 +103,27 @@ def test_uint8_input_equals_float_input_divided_by_255():
 def test_model_plan_is_cached_and_deterministic():
     m, sd, cfg = _build("skyeye_s")
     x = cases.image((1, 3, 96, 96)).cuda()
-    d1, _ = m(x)
+    d1 = m(x)[0].clone()   # the returned tensors are the plan's output buffers (valid until the next call of this shape)
     d2, _ = m(x)
     assert len(m._plans) == 1
     assert torch.equal(d1, d2)
+    m.reuse_output_buffers = False
+    d3, _ = m(x)
+    d4, _ = m(x)
+    assert d3.data_ptr() != d4.data_ptr() and torch.equal(d3, d4) and torch.equal(d3, d1)
 
 
 def test_cuda_graph_replay_matches_eager_plan():
     m, sd, cfg = _build("skyeye_nano_l")
     x = cases.image((1, 3, 128, 128)).cuda()
-    d1, r1 = m(x)
+    assert m.use_cuda_graph and m.reuse_output_buffers   # the README call is the fast path by default
+    m.use_cuda_graph = False
+    d1 = m(x)[0].clone()
     m._plans.clear()
     m.use_cuda_graph = True
-    d2, r2 = m(x)
+    d2 = m(x)[0].clone()
     d3, r3 = m(x)
+    assert m.plan_for(x).graph is not None
     assert torch.equal(d1, d2) and torch.equal(d2, d3)
 
 
@@ -190,3 +197,76 @@ def test_small_and_odd_inputs_run_and_match(variant, shape):
     for a, f in zip(raws, r_f32):
         assert a.shape == f.shape and bool(torch.isfinite(a).all())
         assert _rms(a, f) < 2 * RMS_BOUND[variant], _rms(a, f)
+
+
+def test_reference_default_num_classes_80_runs_end_to_end():
+    """DetectionHead's reference default is num_classes = 80 (detector.py:28): 3 * 85 = 255 head channels through the decode
+    kernel and N * nc = 80 * 3 * (h*w...) slots through the batched NMS (23+ bit slot field at 1280^2)."""
+    import numpy as np
+    from oracle import nms as onms
+    from skyeye.core.detector import construct_model
+    from skyeye.utils.metrics import non_max_suppression
+    cfg = om.get_cfg(dict(om.VARIANTS["skyeye_s"], nc=80))
+    sd = om.make_state_dict(cfg, 0)
+    m = construct_model("skyeye_s.yaml", num_classes=80)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    x = cases.image((2, 3, 96, 160))
+    det, raws = m(x.cuda())
+    torch.cuda.synchronize()
+    d_f32, r_f32 = om.forward(x, sd, cfg)
+    assert det.shape == d_f32.shape == (2, 3 * (12 * 20 + 6 * 10 + 3 * 5), 85)
+    for a, f in zip(raws, r_f32):
+        assert a.shape == f.shape and rel_err(a, f) < BOUND["skyeye_s"]
+    d_own = om.decode([r.cpu() for r in raws], x.shape[2:])
+    assert float((det.cpu() - d_own).abs().max() / d_own.abs().clamp_min(1.0).max()) < 1e-5
+    for kw in (dict(), dict(multi_label=True)):
+        out = non_max_suppression(det, 0.3, 0.5, **kw)
+        ref = onms.non_max_suppression(det.cpu().numpy(), 0.3, 0.5, **kw)
+        assert all(np.array_equal(a.cpu().numpy(), b) for a, b in zip(out, ref))
+    # the slot field widens with N * nc: 100800 boxes x 80 classes (skyeye at 1280^2) = 8.06 M slots
+    big = torch.zeros((1, 100800, 85), device="cuda")
+    big[0, ::997, 4] = 0.9
+    big[0, ::997, 5 + 79] = 0.8
+    big[0, ::997, 0:2] = torch.arange(0, 100800, 997, device="cuda")[:, None].float() * 7.0
+    big[0, ::997, 2:4] = 5.0
+    out = non_max_suppression(big, 0.25, 0.45, multi_label=True)
+    ref = onms.non_max_suppression(big.cpu().numpy(), 0.25, 0.45, multi_label=True)
+    assert np.array_equal(out[0].cpu().numpy(), ref[0]) and out[0].shape[0] > 50
+
+
+def test_cli_validate_runs_as_a_module_on_a_synthetic_folder(tmp_path):
+    """README.md:69: ``python -m skyeye.cli.validate --weights ... --data ... --img-size ...`` in a fresh process, mixed aspect
+    ratios in one batch, --save-txt / --save-conf / --save-json outputs in the formats of validate.py:31-68."""
+    import json
+    import os
+    import subprocess
+    import sys
+    cv2 = pytest.importorskip("cv2")
+    import numpy as np
+    (tmp_path / "data" / "images" / "val").mkdir(parents=True)
+    (tmp_path / "data" / "labels" / "val").mkdir(parents=True)
+    g = cases.rng("cli")
+    for i, (h, w) in enumerate([(200, 320), (320, 320), (240, 320), (320, 200)]):
+        cv2.imwrite(str(tmp_path / "data" / "images" / "val" / f"{i:06d}.png"), g.integers(0, 256, (h, w, 3), dtype=np.uint8))
+        (tmp_path / "data" / "labels" / "val" / f"{i:06d}.txt").write_text("1 0.5 0.5 0.2 0.3\n4 0.25 0.3 0.1 0.1\n")
+    data = tmp_path / "drone.yaml"
+    data.write_text(f"path: {tmp_path / 'data'}\nval: images/val\nnc: 10\nnames: [a, b, c, d, e, f, g, h, i, j]\n")
+    cfg = om.get_cfg("skyeye_s")
+    ckpt = tmp_path / "skyeye_s.pt"
+    torch.save({"state_dict": om.make_state_dict(cfg, 0)}, ckpt)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=os.path.join(root, "skyeye-aerial-object-detection-using-yolo_b200"))
+    r = subprocess.run([sys.executable, "-m", "skyeye.cli.validate", "--weights", str(ckpt), "--data", str(data), "--img-size", "160",
+                        "--batch-size", "2", "--conf-thres", "0.3", "--save-txt", "--save-conf", "--save-json", "--project",
+                        str(tmp_path / "runs"), "--name", "exp"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert set(res) == {"P", "R", "mAP@.5", "mAP@.5:.95"} and all(0.0 <= v <= 1.0 for v in res.values())
+    assert "Loaded" in r.stdout and "Speed:" in (r.stdout + r.stderr)
+    txts = sorted((tmp_path / "runs" / "exp" / "labels").glob("*.txt"))
+    assert [t.stem for t in txts] == [f"{i:06d}" for i in range(4)]
+    row = txts[0].read_text().splitlines()[0].split()
+    assert len(row) == 6 and 0 <= int(row[0]) < 10 and all(0.0 <= float(v) <= 1.0 for v in row[1:])
+    jd = json.loads((tmp_path / "runs" / "exp" / "skyeye_s_predictions.json").read_text())
+    assert jd and set(jd[0]) == {"image_id", "category_id", "bbox", "score"} and isinstance(jd[0]["image_id"], int)

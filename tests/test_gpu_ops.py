@@ -171,6 +171,34 @@ def test_flash_attention_peaky_logits_exercise_lazy_rescale():
     assert rel_err(o.torch().reshape(b, h * w, C), ref) < 2e-2
 
 
+@pytest.mark.parametrize("h,w,heads", [(40, 40, 2), (80, 80, 2)])  # N = 1600 (one query tile per CTA) / 6400 (two)
+def test_flash_attention_late_rescale_in_one_warp_does_not_race_the_epilogue(h, w, heads):
+    """Regression (found by the teacher-forced test on real skyeye_l activations): rows 32..63 of every query tile see
+    their largest logits only in the LAST three key tiles (growing by > 8 in the log2 domain each time), so that one
+    softmax warp takes the O-rescale path late while the other three warps run two tiles ahead into the epilogue.
+    The epilogue used to wait on a per-tile barrier by parity and fell through two phases early."""
+    from skyeye import engine as E
+    b, C, N = 1, heads * 64, h * w
+    qkv = randn(("att_late", h, w), (b, N, 3 * C), 0.5)
+    q, k = qkv[..., :C], qkv[..., C:2 * C]
+    rows = (torch.arange(N) % 128 >= 32) & (torch.arange(N) % 128 < 64)
+    for hd in range(heads):
+        q[:, :, hd * 64] = 0.0
+        q[:, rows, hd * 64] = 4.0
+        k[:, :, hd * 64] = 0.0
+        for t, c in ((3, 16.0), (2, 32.0), (1, 48.0)):   # logits 8, 16, 24 (natural) in the last three 64-key tiles
+            k[:, N - 64 * t:N - 64 * (t - 1), hd * 64] = c
+    qkv = bf16r(qkv)
+    ref = _attn_ref(qkv, heads)
+    qv = E.View(qkv.view(b, h, w, 3 * C).to(torch.bfloat16).cuda().contiguous())
+    for _ in range(5):
+        o = E.new_buffer(b, h, w, C)
+        o.t.zero_()
+        E.flash_attn(qv, o, heads, 1.0 / 8.0)
+        torch.cuda.synchronize()
+        assert rel_err(o.torch().reshape(b, N, C), ref) < TOL
+
+
 @pytest.mark.parametrize("hw", [(64, 96), (160, 128)])
 def test_decode_matches_oracle(hw):
     """process_detections (detector.py:88-145) incl. the [B,na,h,w,no] relayout of raw outputs."""
