@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the batch-1 latency probe (keeps an ncu launch list to the timed steps)")
     ap.add_argument("--no-graph", action="store_true", help="launch the forward plan kernel by kernel instead of replaying its CUDA graph")
+    ap.add_argument("--no-tiled", action="store_true", help="skip the config-4 leg (16 4K frames = 128 tiles, tile-sharded, gather + merge)")
+    ap.add_argument("--tiled-steps", type=int, default=0, help="timed steps of the config-4 leg (default: 4 at N=1, --steps otherwise)")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel table here")
     return ap.parse_args()
 
@@ -386,6 +388,50 @@ def run_b200(args):
         latency = {"p50_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)], "min_ms": lat[0], "samples": len(lat),
                    "scope": f"{args.variant} {S}x{S} batch 1: model(x) + NMS, image resident, CUDA events"}
 
+    # BASELINE config 4 (north_star: "scales >= 7x from 1 to 8 GPUs on tiled 4K frames"): 16 synthetic 3840x2160 frames = 128 tiles of
+    # 1280^2, tiles round-robin over ranks, forward + per-tile NMS with no collective, ONE all_gather of padded rows + counts,
+    # per-frame merge NMS on every rank (skyeye/utils/tiling.TiledDetector).  Strong scaling: the 16 frames are fixed.
+    tiled = None
+    if not args.no_tiled and args.variant == VARIANT and S == H:
+        import hashlib
+        from skyeye.utils.tiling import TiledDetector
+        NF, FH, FW = 16, 2160, 3840
+        import numpy as np
+        frames = torch.from_numpy(np.random.Generator(np.random.PCG64(4242)).integers(0, 256, (NF, 3, FH, FW), dtype=np.uint8)).to(dev)  # same on every rank
+        td = TiledDetector(model, NF, (FH, FW), rank=rank, world=world, conf=CONF, iou=IOU, max_det=MAX_DET, compat="fixed")
+        for _ in range(2):
+            td(frames)
+        torch.cuda.synchronize()
+        tsteps = args.tiled_steps or (4 if world == 1 else max(args.steps, 4))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        slot = 0
+        for _ in range(tsteps):
+            slot = td.step(frames)          # merge of step t (side stream) overlaps the forward of step t+1
+        torch.cuda.current_stream().wait_event(td.ev_done[slot])
+        if tsteps > 1:
+            torch.cuda.current_stream().wait_event(td.ev_done[slot ^ 1])
+        e1.record()
+        torch.cuda.synchronize()
+        ms_t = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_t], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_t = float(t.item())
+        rows_t, cnt_t = td.result(slot)
+        sha = hashlib.sha256(rows_t.cpu().numpy().tobytes() + cnt_t.cpu().numpy().tobytes()).hexdigest()[:16]
+        merge_ms = sum(td.merge_ms(sl) for sl in (0, 1)) / 2
+        tiles_local = td.n_local
+        tiled = {"frames_per_s": NF * tsteps / (ms_t / 1e3), "tiles_per_s": td.n_tiles * tsteps / (ms_t / 1e3), "ms_per_step": ms_t / tsteps,
+                 "steps": tsteps, "frames_per_step": NF, "tiles_per_step": td.n_tiles, "tiles_per_rank": tiles_local,
+                 "ms_gather_merge": merge_ms, "sha256_16": sha, "detections": int(cnt_t.sum()), "scaling": "strong",
+                 "untiled_ms_for_the_same_tiles": ms_step * tiles_local / B,
+                 "config": f"{NF} frames {FW}x{FH} -> {td.T} tiles of 1280^2 per frame (SURVEY D8), tile_id % world, per-tile NMS(conf {CONF}, iou {IOU}, "
+                           f"max_det {MAX_DET}, rows [x1,y1,x2,y2,conf,cls]), one all_gather [{td.n_local_max},{MAX_DET + 1},7] fp32 per rank, merge NMS on "
+                           "every rank; gather + merge of step t on a second stream under the forward of step t+1; frames resident"}
+        del td, frames
+
     launches_per_step = plan.launches + NMS_LAUNCHES
     from skyeye.engine import View
     act_gb = sum(v.t.numel() * v.t.element_size() for v in plan.keep if isinstance(v, View)) / 1e9
@@ -434,6 +480,7 @@ def run_b200(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "parity": parity,
+            "tiled4k": tiled,
             "latency_b1": latency,
             "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in table.items()},
         }

@@ -98,6 +98,12 @@ size_t skb_focus_conv_workspace_bytes(int32_t n, int32_t h, int32_t w);
 int skb_focus_conv_bf16(const void* img, int32_t img_dtype, int32_t n, int32_t h, int32_t w, const void* w_rowtap,
                         const float* bias, const skb_view* y, int32_t cout_pad, int32_t act, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* Same, reading image n in place as the h x w window at (y0, x0) of frame f of `frames` [F,3,frame_h,frame_w]:
+ * tiles_dev = device int32 [n][3] rows (f, y0, x0).  Tiled inference of 4K drone frames (BASELINE config 4; the reference
+ * has no tile code -- nearest call site validate.py:234-256 -- SURVEY.md D8): the tile batch is never materialised. */
+int skb_focus_conv_tiles_bf16(const void* frames, int32_t img_dtype, int32_t frame_h, int32_t frame_w, const int32_t* tiles_dev,
+                              int32_t n, int32_t h, int32_t w, const void* w_rowtap, const float* bias, const skb_view* y,
+                              int32_t cout_pad, int32_t act, void* workspace, size_t workspace_bytes, void* stream);
 /* Inference-time pre-processing in one pass: `letterbox` (skyeye/core/data/augmentation.py:442-496:
  * cv2.resize INTER_LINEAR to new_h x new_w, constant border `pad`) + BGR->RGB + HWC->CHW (detect.py:131-132).
  * src: uint8 [h0][w0][3] BGR (device memory, row pitch src_pitch bytes); dst: uint8 [3][H][W] RGB planes (device) --
@@ -169,6 +175,18 @@ int skb_nms_batched_f32(const float* pred, int32_t b, int32_t n, int32_t nc, flo
                         const int32_t* classes_host, int32_t n_classes, int32_t agnostic, int32_t multi_label,
                         int32_t max_det, int32_t compat, float* out, int32_t* out_count, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* Tiled form of the wrapper (BASELINE config 4): image b is a tile whose origin tile_xy_dev[b] = (x0, y0)
+ * (device int32 [B][2]) is added to the kept rows (columns 0,1 of reference rows; 0..3 of fixed rows) in the kernel's
+ * epilogue, and the rows go, zero padded, with the count in an extra trailing row, straight into the all_gather send buffer:
+ * out_packed fp32 [B][max_det + 1][7], row max_det = [count, 0, ...].  No class filter. */
+int skb_nms_batched_tiles_f32(const float* pred, int32_t b, int32_t n, int32_t nc, float conf_thr, float iou_thr, int32_t agnostic,
+                              int32_t multi_label, int32_t max_det, int32_t compat, const int32_t* tile_xy_dev, float* out_packed,
+                              int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
+/* Gathered per-tile rows -> prediction tensor of the per-frame merge NMS.  gathered: fp32 [world][tiles_per_rank][max_det+1][7]
+ * (rank r holds global tiles r, r + world, ...; global tile = frame * tiles_per_frame + k); pred: fp32
+ * [n_frames][tiles_per_frame * max_det][5 + nc], fed to skb_nms_batched_f32 with the same compat. */
+int skb_tile_merge_pred_f32(const float* gathered, int32_t world, int32_t tiles_per_rank, int32_t n_frames, int32_t tiles_per_frame,
+                            int32_t max_det, int32_t nc, int32_t compat, float* pred, void* stream);
 
 #ifdef __cplusplus
 }

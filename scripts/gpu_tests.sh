@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
 TAG=${1:-t}
 shift
-FILES=${@:-conv ops nms model fullsize}
+FILES=${@:-conv ops nms model fullsize teacher_forced}
 for t in $FILES; do
   timeout 900 python -m pytest tests/test_gpu_$t.py -m gpu -q -rA --tb=short -s > gpurun_out/${TAG}_$t.log 2>&1
   echo "$t exit $?"

@@ -1056,7 +1056,8 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
 // FocusBlock as (padded space-to-depth) + (row-tap implicit GEMM over sliding 128-byte windows)
 // ---------------------------------------------------------------------------------------------
 namespace skb {
-int launch_focus_pad(const void* img, int img_dtype, int n, int h, int w, void* scratch, cudaStream_t st);
+int launch_focus_pad(const void* img, int img_dtype, int n, int h, int w, void* scratch, cudaStream_t st, const int* tiles, int frame_h,
+                     int frame_w);
 }
 
 extern "C" size_t skb_focus_conv_workspace_bytes(int32_t n, int32_t h, int32_t w) {
@@ -1064,15 +1065,34 @@ extern "C" size_t skb_focus_conv_workspace_bytes(int32_t n, int32_t h, int32_t w
     return (size_t)n * (h / 2) * (w / 2 + 4) * 16 * 2 + 256;
 }
 
+static int focus_conv_impl(const void* img, int32_t img_dtype, int32_t n, int32_t h, int32_t w, const void* w_rowtap,
+                           const float* bias, const skb_view* y, int32_t cout_pad, int32_t act, void* workspace,
+                           size_t workspace_bytes, void* stream, const int32_t* tiles, int32_t frame_h, int32_t frame_w);
+
 extern "C" int skb_focus_conv_bf16(const void* img, int32_t img_dtype, int32_t n, int32_t h, int32_t w, const void* w_rowtap,
                                    const float* bias, const skb_view* y, int32_t cout_pad, int32_t act, void* workspace,
                                    size_t workspace_bytes, void* stream) {
+    return focus_conv_impl(img, img_dtype, n, h, w, w_rowtap, bias, y, cout_pad, act, workspace, workspace_bytes, stream, nullptr, 0, 0);
+}
+
+extern "C" int skb_focus_conv_tiles_bf16(const void* frames, int32_t img_dtype, int32_t frame_h, int32_t frame_w, const int32_t* tiles_dev,
+                                         int32_t n, int32_t h, int32_t w, const void* w_rowtap, const float* bias, const skb_view* y,
+                                         int32_t cout_pad, int32_t act, void* workspace, size_t workspace_bytes, void* stream) {
+    SKB_REQUIRE(tiles_dev && frame_h >= h && frame_w >= w, SKB_ERR_ARG, "focus_conv_tiles: tile table / frame %dx%d smaller than the %dx%d tile",
+                frame_h, frame_w, h, w);
+    return focus_conv_impl(frames, img_dtype, n, h, w, w_rowtap, bias, y, cout_pad, act, workspace, workspace_bytes, stream, tiles_dev, frame_h,
+                           frame_w);
+}
+
+static int focus_conv_impl(const void* img, int32_t img_dtype, int32_t n, int32_t h, int32_t w, const void* w_rowtap,
+                           const float* bias, const skb_view* y, int32_t cout_pad, int32_t act, void* workspace,
+                           size_t workspace_bytes, void* stream, const int32_t* tiles, int32_t frame_h, int32_t frame_w) {
     int rc = check_device();
     if (rc != SKB_OK) return rc;
     SKB_REQUIRE(img && w_rowtap && bias && y && y->ptr && workspace, SKB_ERR_ARG, "focus_conv: null argument");
     SKB_REQUIRE(img_dtype == SKB_F32 || img_dtype == SKB_U8, SKB_ERR_ARG, "focus_conv: image dtype must be SKB_F32 or SKB_U8");
     SKB_REQUIRE(n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, SKB_ERR_ARG, "focus_conv: H, W must be even (got %dx%d)", h, w);
-    SKB_REQUIRE(((uintptr_t)img & (img_dtype == SKB_F32 ? 7 : 1)) == 0, SKB_ERR_ARG, "focus_conv: image alignment");
+    SKB_REQUIRE(tiles || ((uintptr_t)img & (img_dtype == SKB_F32 ? 7 : 1)) == 0, SKB_ERR_ARG, "focus_conv: image alignment");
     const int Ho = h / 2, Wo = w / 2, Wp = Wo + 4;
     SKB_REQUIRE(y->dtype == SKB_BF16 && y->n == n && y->h == Ho && y->w == Wo, SKB_ERR_ARG, "focus_conv: output view [%d,%d,%d] != [%d,%d,%d]",
                 y->n, y->h, y->w, n, Ho, Wo);
@@ -1082,7 +1102,7 @@ extern "C" int skb_focus_conv_bf16(const void* img, int32_t img_dtype, int32_t n
     SKB_REQUIRE(workspace_bytes >= skb_focus_conv_workspace_bytes(n, h, w), SKB_ERR_WORKSPACE, "focus_conv: workspace too small");
     void* scratch = (void*)(((uintptr_t)workspace + 127) & ~(uintptr_t)127);
     cudaStream_t st = (cudaStream_t)stream;
-    rc = launch_focus_pad(img, img_dtype, n, h, w, scratch, st);
+    rc = launch_focus_pad(img, img_dtype, n, h, w, scratch, st, tiles, frame_h, frame_w);
     if (rc != SKB_OK) return rc;
 
     ConvParams p;

@@ -69,13 +69,31 @@ __global__ void focus_kernel(const T* __restrict__ img, int N, int H, int W, __n
 }
 
 // Same space-to-depth into the padded 16-channel scratch of skb_focus_conv_bf16: row = [0 | Wo pixels | 0 0 0]
-template <typename T>
 // One CTA per output row (n, oy): no per-element index division (the flat 64-bit i % Wp, i / Wp form spent most of its
 // issue slots on it: 1.7 TB/s).
-__global__ void focus_pad_kernel(const T* __restrict__ img, int N, int H, int W, __nv_bfloat16* __restrict__ y) {
+// TILED = true: image n is a window of a larger frame (4K drone frames cut into 1280^2 tiles): `tiles` holds
+// (frame, y0, x0) per image and the window is read in place -- the tile batch never exists in memory.  Window origins may
+// be odd (x0 = 853), so that variant loads single pixels.
+__device__ __forceinline__ float focus_ld1(const float* p) { return *p; }
+__device__ __forceinline__ float focus_ld1(const uint8_t* p) { return __fdiv_rn((float)*p, 255.0f); }
+template <typename T, bool TILED>
+__global__ void focus_pad_kernel(const T* __restrict__ img, int N, int H, int W, __nv_bfloat16* __restrict__ y,
+                                 const int* __restrict__ tiles, int FH, int FW) {
     const int Ho = H / 2, Wo = W / 2, Wp = Wo + 4;
     const int oy = (int)(blockIdx.x % (unsigned int)Ho);
     const int n = (int)(blockIdx.x / (unsigned int)Ho);
+    const T* src;       // pixel (0, 2*oy, 0) of image n
+    long plane, pitch;  // elements between channel planes / rows
+    if (TILED) {
+        const int f = tiles[3 * n], y0 = tiles[3 * n + 1], x0 = tiles[3 * n + 2];
+        plane = (long)FH * FW;
+        pitch = FW;
+        src = img + (long)f * 3 * plane + (long)(y0 + 2 * oy) * FW + x0;
+    } else {
+        plane = (long)H * W;
+        pitch = W;
+        src = img + (long)n * 3 * plane + (long)(2 * oy) * W;
+    }
     for (int col = threadIdx.x; col < Wp; col += blockDim.x) {
         const long i = ((long)n * Ho + oy) * Wp + col;
         uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
@@ -84,9 +102,15 @@ __global__ void focus_pad_kernel(const T* __restrict__ img, int N, int H, int W,
             float v[12];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const T* base = img + (((long)n * 3 + c) * H + 2 * oy) * W + 2 * ox;
-                const float2 top = focus_ld2(base);
-                const float2 bot = focus_ld2(base + W);
+                const T* base = src + c * plane + 2 * ox;
+                float2 top, bot;
+                if (TILED) {
+                    top = make_float2(focus_ld1(base), focus_ld1(base + 1));
+                    bot = make_float2(focus_ld1(base + pitch), focus_ld1(base + pitch + 1));
+                } else {
+                    top = focus_ld2(base);
+                    bot = focus_ld2(base + pitch);
+                }
                 v[0 * 3 + c] = top.x; v[1 * 3 + c] = bot.x; v[2 * 3 + c] = top.y; v[3 * 3 + c] = bot.y;
             }
             a.x = pack_bf16x2(v[0], v[1]); a.y = pack_bf16x2(v[2], v[3]); a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
@@ -596,12 +620,17 @@ extern "C" int skb_focus_nchw_u8(const uint8_t* img, int32_t n, int32_t h, int32
 }
 
 namespace skb {
-int launch_focus_pad(const void* img, int img_dtype, int n, int h, int w, void* scratch, cudaStream_t st) {
+int launch_focus_pad(const void* img, int img_dtype, int n, int h, int w, void* scratch, cudaStream_t st, const int* tiles,
+                     int frame_h, int frame_w) {
     const int rows = n * (h / 2);  // one CTA per padded output row
-    if (img_dtype == SKB_F32)
-        focus_pad_kernel<float><<<rows, 256, 0, st>>>((const float*)img, n, h, w, (__nv_bfloat16*)scratch);
-    else
-        focus_pad_kernel<uint8_t><<<rows, 256, 0, st>>>((const uint8_t*)img, n, h, w, (__nv_bfloat16*)scratch);
+    __nv_bfloat16* y = (__nv_bfloat16*)scratch;
+    if (tiles) {
+        if (img_dtype == SKB_F32) focus_pad_kernel<float, true><<<rows, 256, 0, st>>>((const float*)img, n, h, w, y, tiles, frame_h, frame_w);
+        else focus_pad_kernel<uint8_t, true><<<rows, 256, 0, st>>>((const uint8_t*)img, n, h, w, y, tiles, frame_h, frame_w);
+    } else {
+        if (img_dtype == SKB_F32) focus_pad_kernel<float, false><<<rows, 256, 0, st>>>((const float*)img, n, h, w, y, nullptr, 0, 0);
+        else focus_pad_kernel<uint8_t, false><<<rows, 256, 0, st>>>((const uint8_t*)img, n, h, w, y, nullptr, 0, 0);
+    }
     SKB_LAUNCH_CHECK();
     return SKB_OK;
 }

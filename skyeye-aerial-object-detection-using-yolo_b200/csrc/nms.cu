@@ -213,6 +213,10 @@ struct BatchedParams {
     int agnostic, multi_label, compat, max_det;
     int capacity;
     int slot_bits;
+    // tiled inference: kept rows are shifted by the tile origin into frame coordinates and written, zero
+    // padded, with the count in an extra trailing row, straight into the all_gather send buffer
+    const int* tile_xy;  // [B][2] = (x0, y0) per image, or null
+    int out_rows;        // rows per image in `out`: max_det, or max_det + 1 (row max_det = [count, 0, ...])
 };
 
 struct Cand {
@@ -258,6 +262,11 @@ nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict_
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // frame-coordinate shift of this image's rows: columns (0, 1) of the reference rows [cx, cy, w, h, ...], columns
+    // (0, 1, 2, 3) of the fixed rows [x1, y1, x2, y2, ...]
+    float shift = 0.0f;
+    if (p.tile_xy && lane < (p.compat ? 4 : 2)) shift = (float)p.tile_xy[2 * b + (lane & 1)];
+    float* out_b = out + (long)b * p.out_rows * 7;
     long off = 0;
     for (int i = 0; i < b; ++i) off += count[i];
     int n = count[b];
@@ -326,7 +335,7 @@ nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict_
                 if (!__any_sync(0xffffffffu, (m & kw) != 0u)) {
                     const int t = surv[s];
                     if (lane == 0) { kx1[kept] = cx1[t]; ky1[kept] = cy1[t]; kx2[kept] = cx2[t]; ky2[kept] = cy2[t]; kar[kept] = car[t]; }
-                    if (lane < 7) out[((long)b * p.max_det + kept) * 7 + lane] = crow[t][lane];
+                    if (lane < 7) out_b[kept * 7 + lane] = __fadd_rn(crow[t][lane], shift);
                     if (lane == (s >> 5)) kw |= 1u << (s & 31);
                     ++kept;
                 }
@@ -337,6 +346,10 @@ nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict_
         __syncthreads();
     }
     if (tid == 0) out_count[b] = s_kept;
+    if (p.out_rows > p.max_det) {  // gather-buffer form: zero the unused rows, append the count row
+        const int kept = s_kept;
+        for (int i = kept * 7 + tid; i < p.out_rows * 7; i += NMS_THREADS) out_b[i] = i == p.max_det * 7 ? (float)kept : 0.0f;
+    }
 }
 
 struct BatchedWs {
@@ -402,9 +415,30 @@ extern "C" size_t skb_nms_batched_workspace_bytes(int32_t b, int32_t n, int32_t 
     return batched_layout(b, n, nc, multi_label, nullptr, nullptr);
 }
 
+static int nms_batched_impl(const float* pred, int32_t b, int32_t n, int32_t nc, float conf_thr, float iou_thr,
+                            const int32_t* classes_host, int32_t n_classes, int32_t agnostic, int32_t multi_label, int32_t max_det,
+                            int32_t compat, float* out, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream,
+                            const int32_t* tile_xy_dev, int32_t out_rows);
+
 extern "C" int skb_nms_batched_f32(const float* pred, int32_t b, int32_t n, int32_t nc, float conf_thr, float iou_thr,
                                    const int32_t* classes_host, int32_t n_classes, int32_t agnostic, int32_t multi_label, int32_t max_det,
                                    int32_t compat, float* out, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+    return nms_batched_impl(pred, b, n, nc, conf_thr, iou_thr, classes_host, n_classes, agnostic, multi_label, max_det, compat, out, out_count,
+                            workspace, workspace_bytes, stream, nullptr, max_det);
+}
+
+extern "C" int skb_nms_batched_tiles_f32(const float* pred, int32_t b, int32_t n, int32_t nc, float conf_thr, float iou_thr, int32_t agnostic,
+                                         int32_t multi_label, int32_t max_det, int32_t compat, const int32_t* tile_xy_dev, float* out_packed,
+                                         int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+    SKB_REQUIRE(tile_xy_dev, SKB_ERR_ARG, "nms_batched_tiles: null tile origin table");
+    return nms_batched_impl(pred, b, n, nc, conf_thr, iou_thr, nullptr, 0, agnostic, multi_label, max_det, compat, out_packed, out_count,
+                            workspace, workspace_bytes, stream, tile_xy_dev, max_det + 1);
+}
+
+static int nms_batched_impl(const float* pred, int32_t b, int32_t n, int32_t nc, float conf_thr, float iou_thr,
+                            const int32_t* classes_host, int32_t n_classes, int32_t agnostic, int32_t multi_label, int32_t max_det,
+                            int32_t compat, float* out, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream,
+                            const int32_t* tile_xy_dev, int32_t out_rows) {
     int rc = check_device();
     if (rc != SKB_OK) return rc;
     SKB_REQUIRE(pred && out && out_count && workspace && b > 0 && n > 0 && nc >= 0, SKB_ERR_ARG, "nms_batched: bad arguments");
@@ -439,10 +473,70 @@ extern "C" int skb_nms_batched_f32(const float* pred, int32_t b, int32_t n, int3
     BatchedParams bp;
     bp.pred = pred; bp.B = b; bp.N = n; bp.nc = nc; bp.no = nc + 5; bp.iou = iou_thr; bp.agnostic = agnostic; bp.multi_label = multi_label;
     bp.compat = compat; bp.max_det = max_det; bp.capacity = (int)cap; bp.slot_bits = slot_bits;
+    bp.tile_xy = tile_xy_dev; bp.out_rows = out_rows;
     constexpr int kMaskBytes = NMS_THREADS * (NMS_THREADS / 32) * (int)sizeof(unsigned int);
     static PerDeviceOnce attr_once;
     if (attr_once.first()) SKB_CUDA(cudaFuncSetAttribute(nms_keptlist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaskBytes));
     nms_keptlist_kernel<<<b, NMS_THREADS, kMaskBytes, st>>>(bp, ws.keys_out, ws.count, out, out_count);
+    SKB_LAUNCH_CHECK();
+    return SKB_OK;
+}
+
+
+// =============================================================================================
+// (3) cross-tile merge (BASELINE config 4; NOT IN REFERENCE): the all_gather'ed per-tile rows
+//     [world][tiles_per_rank][max_det + 1][7] (rank r holds global tiles r, r + world, ...) are re-expressed as a prediction
+//     tensor [frames][tiles_per_frame * max_det][5 + nc] so that the SAME wrapper kernels (metrics.py:361-457 semantics)
+//     perform the per-frame merge NMS.  Reference rows [cx,cy,w,h,obj,cls_prob,cls_id] are copied with the class probability
+//     at column 5 + cls_id (best-class selection recovers (cls_prob, cls_id) exactly); fixed rows [x1,y1,x2,y2,conf,cls] become
+//     centre form with obj = conf and class probability 1 (conf * 1 is exact).  Rows beyond a tile's count stay zero
+//     (objectness 0 -> dropped by the confidence filter).  One thread per output float: coalesced stores.
+// =============================================================================================
+namespace skb {
+__global__ void tile_merge_pred_kernel(const float* __restrict__ gathered, int world, int tiles_per_rank, int n_tiles, int tiles_per_frame,
+                                       int max_det, int nc, int compat, float* __restrict__ pred) {
+    const int no = 5 + nc;
+    const long total = (long)n_tiles * max_det * no;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % no);
+        const long rj = i / no;
+        const int j = (int)(rj % max_det);
+        const int g = (int)(rj / max_det);  // global tile id = frame * tiles_per_frame + k: pred rows are already in (frame, k, j) order
+        const float* src = gathered + ((long)(g % world) * tiles_per_rank + g / world) * (max_det + 1) * 7;
+        float v = 0.0f;
+        if (j < (int)src[max_det * 7]) {
+            const float* r = src + j * 7;
+            if (compat == 0) {
+                if (c < 5) v = r[c];
+                else if (nc == 1) v = 1.0f;
+                else if (c - 5 == (int)r[6]) v = r[5];
+            } else {
+                if (c == 0) v = __fmul_rn(__fadd_rn(r[0], r[2]), 0.5f);
+                else if (c == 1) v = __fmul_rn(__fadd_rn(r[1], r[3]), 0.5f);
+                else if (c == 2) v = __fsub_rn(r[2], r[0]);
+                else if (c == 3) v = __fsub_rn(r[3], r[1]);
+                else if (c == 4) v = r[4];
+                else if (c - 5 == (int)r[5]) v = 1.0f;
+            }
+        }
+        pred[i] = v;
+    }
+}
+}  // namespace skb
+
+extern "C" int skb_tile_merge_pred_f32(const float* gathered, int32_t world, int32_t tiles_per_rank, int32_t n_frames, int32_t tiles_per_frame,
+                                       int32_t max_det, int32_t nc, int32_t compat, float* pred, void* stream) {
+    int rc = check_device();
+    if (rc != SKB_OK) return rc;
+    const long n_tiles = (long)n_frames * tiles_per_frame;
+    SKB_REQUIRE(gathered && pred && world >= 1 && tiles_per_rank >= 1 && n_frames >= 1 && tiles_per_frame >= 1 && max_det >= 1 && nc >= 1 &&
+                    (compat == 0 || compat == 1) && (long)world * tiles_per_rank >= n_tiles,
+                SKB_ERR_ARG, "tile_merge_pred: bad arguments (world %d x %d tiles per rank < %ld tiles)", world, tiles_per_rank, n_tiles);
+    const long total = n_tiles * max_det * (5 + nc);
+    long g = (total + 255) / 256;
+    const long gcap = (long)num_sms() * 16;
+    tile_merge_pred_kernel<<<(int)(g > gcap ? gcap : g), 256, 0, (cudaStream_t)stream>>>(gathered, world, tiles_per_rank, (int)n_tiles,
+                                                                                          tiles_per_frame, max_det, nc, compat, pred);
     SKB_LAUNCH_CHECK();
     return SKB_OK;
 }

@@ -88,6 +88,8 @@ _SIGNATURES = {
     "skb_focus_conv_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "skb_focus_conv_bf16": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, POINTER(skb_view),
                                       c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
+    "skb_focus_conv_tiles_bf16": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                            POINTER(skb_view), c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
     "skb_letterbox_u8": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                    c_int32, c_void_p]),
     "skb_maxpool5_bf16": (c_int32, [POINTER(skb_view), POINTER(skb_view), c_void_p]),
@@ -108,6 +110,9 @@ _SIGNATURES = {
     "skb_nms_batched_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "skb_nms_batched_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_float, c_float, POINTER(c_int32), c_int32,
                                       c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "skb_nms_batched_tiles_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_int32, c_int32, c_int32, c_int32,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "skb_tile_merge_pred_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -136,6 +136,11 @@ class FocusBlock(nn.Module):
         ho, wo = h // 2, w // 2
         flops = 2.0 * n * ho * wo * c.out_channels * 9 * 12
         nbytes = 3.0 * n * h * w + 2.0 * (2.0 * n * ho * (wo + 4) * 16) + 2.0 * n * ho * wo * c.out_channels  # uint8 image
+        if plan.tile_src is not None:  # tiles of larger frames read in place through a (frame, y0, x0) table
+            table = plan.tile_src
+            plan.add(name, lambda s: L.E.focus_conv_tiles(img_holder[0], table, (h, w), pw, out, ws, ACT_SILU, s), "conv", flops, nbytes, 2,
+                     outs=[dict(view=out, label=L.ref(c))])
+            return out
         plan.add(name, lambda s: L.E.focus_conv(img_holder[0], pw, out, ws, ACT_SILU, s), "conv", flops, nbytes, 2,
                  outs=[dict(view=out, label=L.ref(c))])
         return out

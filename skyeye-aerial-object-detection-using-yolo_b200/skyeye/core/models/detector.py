@@ -278,10 +278,11 @@ class SkyEyeDetector(nn.Module):
         feats = self.backbone.lower(plan, self._img, n, h, w, outs)
         return self.neck.lower(plan, feats, bufs)
 
-    def _build_plan(self, n, h, w, device) -> Plan:
+    def _build_plan(self, n, h, w, device, tile_table=None) -> Plan:
         if h % 32 or w % 32:
             raise ValueError(f"input H, W must be multiples of 32 (got {h}x{w}); letterbox first")
         plan = Plan(device)
+        plan.tile_src = tile_table
         for name, m in self.named_modules():  # reference state-dict paths label the plan's outputs (Plan.run_teacher_forced)
             m._ref = name
         feats = self._lower_features(plan, n, h, w)
@@ -320,6 +321,35 @@ class SkyEyeDetector(nn.Module):
                 plan.replay()
             else:
                 self._img[0] = xin
+                plan.run()
+        if self.reuse_output_buffers:
+            return plan.det, plan.raw_out
+        return plan.det.clone(), [r.clone() for r in plan.raw_out]
+
+    @torch.no_grad()
+    def forward_tiles(self, frames: torch.Tensor, tiles: torch.Tensor, tile_hw=(1280, 1280)):
+        """forward() on windows of larger frames WITHOUT materialising the tile batch (tiled inference of 4K drone frames,
+        SURVEY.md D8): frames uint8 / fp32 CUDA [F,3,FH,FW], tiles int32 [n,3] rows (frame, y0, x0).  Image i of the returned
+        (detections, raw_outputs) is the tile_hw window at tiles[i]; coordinates are tile-local.  The plan (and its CUDA
+        graph) is bound to the frame buffer's address and owns a device copy of the table, refreshed on every call."""
+        if not (frames.is_cuda and frames.dim() == 4 and frames.is_contiguous() and frames.dtype in (torch.uint8, torch.float32)):
+            raise RuntimeError("forward_tiles needs a contiguous uint8 / fp32 CUDA frame tensor [F,3,H,W]")
+        n, (th, tw) = int(tiles.shape[0]), tile_hw
+        key = ("tiles", n, th, tw, tuple(frames.shape), frames.dtype, frames.device.index, frames.data_ptr())
+        with torch.cuda.device(frames.device):
+            plan = self._plans.get(key)
+            if plan is None:
+                table = torch.zeros((n, 3), dtype=torch.int32, device=frames.device)
+                plan = self._build_plan(n, th, tw, frames.device, tile_table=table)
+                plan.table = table
+                self._plans[key] = plan
+            plan.table.copy_(tiles.to(torch.int32), non_blocking=True)
+            self._img[0] = frames
+            if self.use_cuda_graph:
+                if plan.graph is None:
+                    plan.capture()
+                plan.replay()
+            else:
                 plan.run()
         if self.reuse_output_buffers:
             return plan.det, plan.raw_out

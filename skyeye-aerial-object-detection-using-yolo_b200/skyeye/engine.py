@@ -145,6 +145,19 @@ def focus_conv(img: torch.Tensor, pw: PackedFocusConv, y: View, ws: torch.Tensor
                                         _stream_ptr() if stream is None else stream), "skb_focus_conv_bf16")
 
 
+def focus_conv_tiles(frames: torch.Tensor, tiles: torch.Tensor, tile_hw, pw: PackedFocusConv, y: View, ws: torch.Tensor,
+                     act: int = ACT_SILU, stream=None) -> None:
+    """FocusBlock.forward on windows of larger frames read in place: frames [F,3,FH,FW] (uint8 / fp32), tiles int32 CUDA
+    [n,3] rows (frame, y0, x0); image i of the batch is the tile_hw window at tiles[i] (SURVEY.md D8 tiling)."""
+    assert frames.dtype in (torch.float32, torch.uint8) and frames.is_contiguous() and frames.dim() == 4 and frames.shape[1] == 3
+    assert tiles.dtype == torch.int32 and tiles.is_cuda and tiles.is_contiguous() and tiles.dim() == 2 and tiles.shape[1] == 3
+    n = tiles.shape[0]
+    N.check(N.lib().skb_focus_conv_tiles_bf16(frames.data_ptr(), SKB_F32 if frames.dtype == torch.float32 else N.SKB_U8,
+                                              frames.shape[2], frames.shape[3], tiles.data_ptr(), n, int(tile_hw[0]), int(tile_hw[1]),
+                                              pw.w.data_ptr(), pw.b.data_ptr(), y.ref, pw.cout_pad, act, ws.data_ptr(), ws.numel(),
+                                              _stream_ptr() if stream is None else stream), "skb_focus_conv_tiles_bf16")
+
+
 # ----------------------------------------------------------------------------------------------
 # eager op wrappers (one native call each)
 # ----------------------------------------------------------------------------------------------
@@ -226,6 +239,7 @@ class Plan:
         self.keep = []  # buffers / packed weights kept alive
         self.graph = None
         self.n_launch_calls = 0
+        self.tile_src = None  # (frames holder [tensor], tile table int32 CUDA [n,3]) when the images are windows of larger frames
 
     def buf(self, n, h, w, c, dtype=torch.bfloat16) -> View:
         v = new_buffer(n, h, w, c, dtype, self.device)

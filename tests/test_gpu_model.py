@@ -33,11 +33,12 @@ pytestmark = pytest.mark.gpu
 # 6e-7 in fp32-accumulate mode (scripts/probe_numerics.py), but every stored activation is re-rounded
 # to bf16 and a sub-ulp difference flips roundings (error sqrt(delta*ulp)), so any two bf16 pipelines
 # (this one, the emulating oracle, PyTorch autocast) sit at mutual distance ~ the bf16 noise floor.
-BOUND = {"skyeye_s": 2.5e-2, "skyeye_m": 3e-2, "skyeye_nano_l": 1.2e-1, "skyeye_l": 1.5e-1}
-RMS_BOUND = {"skyeye_s": 1e-2, "skyeye_m": 2e-2, "skyeye_nano_l": 3e-2, "skyeye_l": 9e-2}
+# skyeye_l measured on B200 (r2b): vs fp32 max 6.3-11.1 %, rms 2.1-9.0 %; vs the emulating oracle max 4.2-9.0 %
+BOUND = {"skyeye_s": 2.5e-2, "skyeye_m": 3e-2, "skyeye_nano_l": 1.2e-1, "skyeye_l": 1.6e-1}
+RMS_BOUND = {"skyeye_s": 1e-2, "skyeye_m": 2e-2, "skyeye_nano_l": 3e-2, "skyeye_l": 1.2e-1}
 # skyeye_l vs the oracle with the SAME bf16 storage points (what is left is accumulation order + intrinsics, amplified by the
 # random network's ~1.5x-per-stage sensitivity; the oracle's own bf16-vs-fp32 distance is 8 % max / 5.5 % rms at 640x640)
-EMU_BOUND = {"skyeye_l": 1.5e-1}
+EMU_BOUND = {"skyeye_l": 1.3e-1}
 EMU_RMS_BOUND = {"skyeye_l": 9e-2}
 
 
@@ -75,7 +76,7 @@ def test_model_matches_oracle(variant, shape):
         assert a.shape == f.shape
         ee, ef = rel_err(a, e), rel_err(a, f)
         print(f"{variant} {shape} level {i}: max-rel vs emu {ee:.3e} vs fp32 {ef:.3e} (oracle emu vs fp32 {rel_err(e, f):.3e}); "
-              f"rms vs fp32 {_rms(a, f):.3e}")
+              f"rms vs fp32 {_rms(a, f):.3e} vs emu {_rms(a, e):.3e}")
         assert ef < BOUND[variant], (i, ef)
         assert ee < EMU_BOUND.get(variant, BOUND[variant]), (i, ee)
         assert _rms(a, f) < RMS_BOUND[variant], (i, _rms(a, f))

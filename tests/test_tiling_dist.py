@@ -44,8 +44,8 @@ def _fake_detect(tiles):
     return det
 
 
-def _oracle_nms_padded(pred, conf, iou, max_detections=300):
-    out = onms.non_max_suppression(pred.numpy(), conf, iou, max_detections=max_detections)
+def _oracle_nms_padded(pred, conf, iou, max_detections=300, compat="reference"):
+    out = onms.non_max_suppression(pred.numpy(), conf, iou, max_detections=max_detections, compat=compat)
     rows = torch.zeros((pred.shape[0], max_detections, 7))
     cnt = torch.zeros(pred.shape[0], dtype=torch.int32)
     for b, o in enumerate(out):
@@ -63,8 +63,11 @@ def _run(rank, world, port, q):
     if world > 1:
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         dist.init_process_group("gloo", rank=rank, world_size=world)
-    rows, cnt = tiling.tiled_detect(_frames(), _fake_detect, _oracle_nms_padded, nc=10, rank=rank, world=world, max_batch=3)
-    q.put((rank, rows.numpy(), cnt.numpy()))
+    out = []
+    for compat in ("fixed", "reference"):
+        rows, cnt = tiling.tiled_detect(_frames(), _fake_detect, _oracle_nms_padded, nc=10, rank=rank, world=world, max_batch=3, compat=compat)
+        out += [rows.numpy(), cnt.numpy()]
+    q.put((rank, *out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -82,16 +85,38 @@ def test_tiled_detect_is_world_size_invariant_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     _run(0, 1, 0, q)
-    _, rows1, cnt1 = q.get()
-    assert cnt1.sum() > 0
+    _, *one = q.get()
+    assert one[1].sum() > 0 and one[3].sum() > 0
     port = _free_port()
     procs = [ctx.Process(target=_run, args=(r, 2, port, q)) for r in range(2)]
     [p.start() for p in procs]
     res = [q.get(timeout=120) for _ in range(2)]
     [p.join(timeout=60) for p in procs]
-    for _, rows2, cnt2 in res:
-        assert np.array_equal(cnt1, cnt2)
-        assert np.array_equal(rows1, rows2)  # identical detections on every rank, independent of world size
+    for _, *two in res:
+        for a, b in zip(one, two):
+            assert np.array_equal(a, b)  # identical detections on every rank, independent of world size, in both row semantics
+
+
+def test_object_straddling_two_tiles_is_merged_into_one_box():
+    """One object in the overlap band of two horizontally adjacent tiles is detected by both (in tile-local coordinates);
+    the cross-tile merge must return ONE box in frame coordinates (compat="fixed": corner boxes).  Under the reference
+    wrapper's reading of (cx, cy, w, h) as corners nothing overlaps in frame coordinates and both copies survive."""
+    origins = [(0, 0), (0, 853)]
+    frames = torch.zeros((1, 3, 1280, 2133))
+    cx, cy, w, h = 1000.0, 600.0, 80.0, 60.0          # frame coordinates: inside both tiles (853 <= x < 1280)
+
+    def detect(tiles):
+        det = torch.zeros((tiles.shape[0], 4, 15))
+        for i, (y0, x0) in enumerate(origins[: tiles.shape[0]]):
+            det[i, 0, :5] = torch.tensor([cx - x0, cy - y0, w, h, 0.9 - 0.05 * i])
+            det[i, 0, 5 + 3] = 0.8
+        return det
+
+    rows, cnt = tiling.tiled_detect(frames, detect, _oracle_nms_padded, nc=10, origins=origins, compat="fixed")
+    assert int(cnt[0]) == 1
+    assert torch.allclose(rows[0, 0, :6], torch.tensor([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2, 0.9 * 0.8, 3.0]), atol=1e-4)
+    rows_r, cnt_r = tiling.tiled_detect(frames, detect, _oracle_nms_padded, nc=10, origins=origins, compat="reference")
+    assert int(cnt_r[0]) == 2   # the quirk: duplicates are not merged
 
 
 def test_merge_prediction_roundtrip_recovers_rows():
