@@ -117,6 +117,13 @@ def test_folder_loader_letterboxes_and_maps_labels(tmp_path):
     img, targets, paths, shapes = batches[0]
     assert img.dtype == torch.uint8 and img.shape[0] == 2 and img.shape[1] == 3 and img.shape[2] % 32 == 0 and img.shape[3] % 32 == 0
     assert targets.shape == (4, 6) and set(targets[:, 0].tolist()) == {0.0, 1.0}
-    # image 0: 100x200 -> gain 0.64 -> 64x128, padded to 64x128: centre stays at the centre
+    # Mixed aspect ratios in one batch: image 0 is 100x200 -> gain 0.64 -> 64x128, image 1 is 120x120 -> 128x128, so
+    # the batch frame is 128x128 and image 0 sits in its top half.  Targets are normalised by the BATCH frame (validate() scales
+    # them back by it): image 0's centre label lands at pixel (64, 32) of the frame, not at the frame centre.
+    H, W = img.shape[2], img.shape[3]
+    assert (H, W) == (128, 128)
     t0 = targets[targets[:, 0] == 0][0]
-    assert abs(float(t0[2]) - 0.5) < 1e-6 and abs(float(t0[3]) - 0.5) < 0.02 and shapes[0][0] == (100, 200)
+    assert abs(float(t0[2]) * W - 64.0) < 1e-3 and abs(float(t0[3]) * H - 32.0) < 1e-3 and shapes[0][0] == (100, 200)
+    assert abs(float(t0[4]) * W - 0.2 * 128) < 1e-3 and abs(float(t0[5]) * H - 0.4 * 64) < 1e-3
+    t1 = targets[targets[:, 0] == 1][0]   # image 1 fills the frame: its centre label stays at the centre
+    assert abs(float(t1[2]) - 0.5) < 1e-3 and abs(float(t1[3]) - 0.5) < 1e-3
