@@ -38,7 +38,7 @@ constexpr int ATT_Q_BYTES = ATT_BQ * ATT_D * 2;     // 16 KB
 constexpr int ATT_KV_BYTES = ATT_BKV * ATT_D * 2;   // 8 KB
 constexpr int ATT_ONES_BYTES = ATT_BKV * 128;       // 8 KB of bf16 1.0: extra B columns that make the PV MMA emit the row sums
 constexpr int ATT_ON = ATT_D + 16;                  // PV accumulator width: 64 output dims + 16 copies of sum_k P
-constexpr int ATT_POLY_DEFAULT = 8;                 // exponentials per 64 evaluated on the FMA pipes (0, 8, 16, 24, 32)
+constexpr int ATT_POLY_DEFAULT = 16;                // exponentials per 64 evaluated on the FMA pipes (0, 8, 16, 24, 32)
 
 // NQ = query tiles (of 128 rows) per CTA.  NQ = 1: 192 threads, 2 CTAs per SM.  NQ = 2: ONE CTA per SM whose two
 // query tiles share the K/V stream in shared memory (half the K/V bytes from L2 and half the TMA writes).  Each query
@@ -127,7 +127,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t slot = bar0 + 8u * (8 * NQ + 2 * KVS);
     volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - raw));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
     const int qt0 = blockIdx.x * NQ, head = blockIdx.y, b = blockIdx.z;
     const int T = p.T;
 
@@ -153,14 +153,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *slot_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *slot_ptr, 0);
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            for (int g = 0; g < NQ; ++g) {
-                mbar_expect_tx(q_full(g), ATT_Q_BYTES);
-                tma_load_3d(sQ + g * ATT_Q_BYTES, &tmQ, q_full(g), head * ATT_D, (qt0 + g) * ATT_BQ, b);
+        // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+        {
+            const bool lead = elect_one();
+            if (lead) {
+                for (int g = 0; g < NQ; ++g) {
+                    mbar_expect_tx(q_full(g), ATT_Q_BYTES);
+                    tma_load_3d(sQ + g * ATT_Q_BYTES, &tmQ, q_full(g), head * ATT_D, (qt0 + g) * ATT_BQ, b);
+                }
             }
             long long pf_tma = 0;
             for (int j = 0; j < T; ++j) {
@@ -170,11 +173,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 if (PROF) c0 = clock64();
                 mbar_wait(kv_empty(s), (u & 1u) ^ 1u);
                 if (PROF) pf_tma += clock64() - c0;
-                mbar_expect_tx(kv_full(s), 2 * ATT_KV_BYTES);
-                tma_load_3d(sK0 + s * ATT_KV_BYTES, &tmKV, kv_full(s), p.C + head * ATT_D, j * ATT_BKV, b);
-                tma_load_3d(sV0 + s * ATT_KV_BYTES, &tmKV, kv_full(s), 2 * p.C + head * ATT_D, j * ATT_BKV, b);
+                if (lead) {
+                    mbar_expect_tx(kv_full(s), 2 * ATT_KV_BYTES);
+                    tma_load_3d(sK0 + s * ATT_KV_BYTES, &tmKV, kv_full(s), p.C + head * ATT_D, j * ATT_BKV, b);
+                    tma_load_3d(sV0 + s * ATT_KV_BYTES, &tmKV, kv_full(s), 2 * p.C + head * ATT_D, j * ATT_BKV, b);
+                }
             }
-            if (PROF) {
+            if (PROF && lead) {
                 atomicAdd(&g_att_prof[10], (unsigned long long)pf_tma);
                 atomicAdd(&g_att_prof[11], (unsigned long long)T);
             }
@@ -196,7 +201,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             mbar_wait(kv_full(s), (uint32_t)(j / KVS) & 1u);
             if (PROF) c1 = clock64();
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {  // a warp-uniform branch: the MMA operands stay in uniform registers (no per-instruction R2UR loop)
                 const uint64_t bd = umma_desc(sK0 + s * ATT_KV_BYTES, 16, 1024, UMMA_SW128);
 #pragma unroll
                 for (int k = 0; k < ATT_D / 16; ++k)  // 16 bf16 of A = 8 TMEM columns
@@ -218,7 +223,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             mbar_wait(p_full(g, sb), (uint32_t)(j >> 1) & 1u);
             if (PROF) { c1 = clock64(); pf_hop += c1 - stamp[2 * g + sb]; }
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
                 // V tile [64 keys][64 d]: MN-major, 128-byte rows, 8-row groups 1024 B apart, 16 keys per MMA = 2048 B.
                 // N = 80: the second 64-wide N atom (leading-dimension offset) is the all-ones tile, so columns
                 // 64..79 of the accumulator receive sum_k P[q][k] -- the softmax denominator comes out of the
@@ -404,6 +409,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+
 }  // namespace skb
 
 using namespace skb;
@@ -432,10 +438,10 @@ extern "C" int skb_flash_attn_bf16(const skb_view* qkv, const skb_view* o, int32
     p.scale_log2 = scale * 1.4426950408889634f;
     p.out = (__nv_bfloat16*)o->ptr; p.out_pitch = o->pitch;
     static int poly = -1, nq_force = 0;
-    if (poly < 0) {  // tuning knobs (not part of the ABI): SKB_ATT_POLY in {0, 8, 16}, SKB_ATT_NQ in {1, 2}
+    if (poly < 0) {  // tuning knobs (not part of the ABI): SKB_ATT_POLY in {0, 8, 16, 24, 32}, SKB_ATT_NQ in {1, 2}
         const char* e = getenv("SKB_ATT_POLY");
         int pv = e ? atoi(e) : ATT_POLY_DEFAULT;
-        if (pv != 0 && pv != 8 && pv != 16) pv = ATT_POLY_DEFAULT;
+        if (pv != 0 && pv != 8 && pv != 16 && pv != 24 && pv != 32) pv = ATT_POLY_DEFAULT;
         e = getenv("SKB_ATT_NQ");
         nq_force = e ? atoi(e) : 0;
         poly = pv;
@@ -445,6 +451,10 @@ extern "C" int skb_flash_attn_bf16(const skb_view* qkv, const skb_view* o, int32
         SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
         SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
         SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<24, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2>::SMEM));
+        SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2>::SMEM));
         SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2>::SMEM));
         SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2>::SMEM));
         SKB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2>::SMEM));
@@ -467,6 +477,8 @@ extern "C" int skb_flash_attn_bf16(const skb_view* qkv, const skb_view* o, int32
         switch (poly) {
             case 0: flash_attn_kernel<0, 2><<<grid, AttCfg<2>::THREADS, AttCfg<2>::SMEM, st>>>(tmQ, tmKV, p); break;
             case 16: flash_attn_kernel<16, 2><<<grid, AttCfg<2>::THREADS, AttCfg<2>::SMEM, st>>>(tmQ, tmKV, p); break;
+            case 24: flash_attn_kernel<24, 2><<<grid, AttCfg<2>::THREADS, AttCfg<2>::SMEM, st>>>(tmQ, tmKV, p); break;
+            case 32: flash_attn_kernel<32, 2><<<grid, AttCfg<2>::THREADS, AttCfg<2>::SMEM, st>>>(tmQ, tmKV, p); break;
             default: flash_attn_kernel<8, 2><<<grid, AttCfg<2>::THREADS, AttCfg<2>::SMEM, st>>>(tmQ, tmKV, p); break;
         }
     } else {
@@ -474,6 +486,8 @@ extern "C" int skb_flash_attn_bf16(const skb_view* qkv, const skb_view* o, int32
         switch (poly) {
             case 0: flash_attn_kernel<0, 1><<<grid, AttCfg<1>::THREADS, AttCfg<1>::SMEM, st>>>(tmQ, tmKV, p); break;
             case 16: flash_attn_kernel<16, 1><<<grid, AttCfg<1>::THREADS, AttCfg<1>::SMEM, st>>>(tmQ, tmKV, p); break;
+            case 24: flash_attn_kernel<24, 1><<<grid, AttCfg<1>::THREADS, AttCfg<1>::SMEM, st>>>(tmQ, tmKV, p); break;
+            case 32: flash_attn_kernel<32, 1><<<grid, AttCfg<1>::THREADS, AttCfg<1>::SMEM, st>>>(tmQ, tmKV, p); break;
             default: flash_attn_kernel<8, 1><<<grid, AttCfg<1>::THREADS, AttCfg<1>::SMEM, st>>>(tmQ, tmKV, p); break;
         }
     }

@@ -208,7 +208,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t slot = bar0 + 8u * (2 * STAGES + 4 + Cfg::EPI_GROUPS * NB);
     volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - raw));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Warp-uniform role index (a shuffle result is uniform to the compiler) and ONE elected lane per warp for every
+    // asynchronous issue (TMA, tcgen05.mma, commits): inside an `if (lane == 0)` region the compiler cannot prove that a
+    // single thread is active and wraps every UTMALDG / UTCHMMA in an ELECT + R2UR "waterfall" loop, which cost the issuing
+    // thread 100-160 cycles per instruction (attention: 640 -> 260 cycles per 4 MMAs once removed, profiles/r2b_uniform_issue.md).
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const bool lead = elect_one();
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -237,7 +242,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (NCTA == 2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
     else __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *slot_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *slot_ptr, 0);
     // Everything above (barrier init, TMEM allocation, descriptor prefetch) touched no global data and may have
     // overlapped the previous kernel's tail; from here on its outputs are read.
     pdl_launch_dependents();
@@ -251,7 +256,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // arms the stage's barrier with the total byte count and loads A, warp 10 loads B; B's bytes may
         // complete first (a transiently negative tx-count), the phase cannot complete before the arm.
         const bool loads_a = warp == 0;
-        if (lane == 0) {
+        {
             int stage = 0;
             uint32_t phase = 0;
             int tr_n = 0;
@@ -268,17 +273,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     // pair: both CTAs' bytes complete on the LEADER's full barrier (its single arrival carries the total)
                     const uint32_t fb = NCTA == 2 ? mapa_shared(full(stage), 0) : full(stage);
                     if (loads_a) {
-                        SKB_TR(0, it);
-                        if (leader) mbar_expect_tx(full(stage), (uint32_t)NCTA * (uint32_t)(p.a_box_bytes + Cfg::B_BYTES));
-                        if (NCTA == 2)
-                            tma_load_5d_pair(sA0 + stage * Cfg::A_BYTES, &tmA, fb, t_coff + cc * BK, w0 + t_dw, t_ph, h0 + t_dh, n0);
-                        else
-                            tma_load_5d(sA0 + stage * Cfg::A_BYTES, &tmA, fb, t_coff + cc * BK, w0 + t_dw, t_ph, h0 + t_dh, n0);
+                        if (lead) {
+                            SKB_TR(0, it);
+                            if (leader) mbar_expect_tx(full(stage), (uint32_t)NCTA * (uint32_t)(p.a_box_bytes + Cfg::B_BYTES));
+                            if (NCTA == 2)
+                                tma_load_5d_pair(sA0 + stage * Cfg::A_BYTES, &tmA, fb, t_coff + cc * BK, w0 + t_dw, t_ph, h0 + t_dh, n0);
+                            else
+                                tma_load_5d(sA0 + stage * Cfg::A_BYTES, &tmA, fb, t_coff + cc * BK, w0 + t_dw, t_ph, h0 + t_dh, n0);
+                        }
                         if (++cc == p.cchunks) {  // next tap: its coordinates load under the next barrier wait
                             cc = 0;
                             if (++tap < 9) { t_coff = p.tap_coff[tap]; t_dw = p.tap_dw[tap]; t_ph = p.tap_ph[tap]; t_dh = p.tap_dh[tap]; }
                         }
-                    } else {
+                    } else if (lead) {
                         if (NCTA == 2) tma_load_2d_pair(sB0 + stage * Cfg::B_BYTES, &tmB, fb, it * BK, nb * BN + cta_rank * (BN / 2));
                         else tma_load_2d(sB0 + stage * Cfg::B_BYTES, &tmB, fb, it * BK, nb * BN);
                     }
@@ -298,12 +305,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int tile = work0; leader && tile < p.total_tiles; tile += wstride) {
             mbar_wait(tempty(as), aphase ^ 1);
             tc_fence_after();
-            if (lane == 0) SKB_TR(1, 1000);
+            if (lead) SKB_TR(1, 1000);
             const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
             for (int it = 0; it < p.k_iters; ++it) {
                 mbar_wait(full(stage), phase);
                 tc_fence_after();
-                if (lane == 0) {
+                if (lead) {
                     SKB_TR(1, it);
                     const uint64_t ad = umma_desc(sA0 + stage * Cfg::A_BYTES, 16, SBO, SW);
                     const uint64_t bd = umma_desc(sB0 + stage * Cfg::B_BYTES, 16, SBO, SW);
@@ -339,7 +346,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;               // accumulator row = pixel of the tile = TMEM lane
         const int tg = (int)threadIdx.x - 64 - g * GT;
-        const bool T0 = tg == 0;                   // issues the group's TMA stores / residual prefetches
+        const bool T0 = ((warp - 2) & 3) == 0 && lead;  // one elected lane of the group's first warp issues its TMA stores / residual prefetches
         const int barid = 1 + g;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const uint32_t ebuf_g = ebuf0 + (uint32_t)(g * NB) * Cfg::EPI_BUF;
@@ -546,7 +553,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t slot = bar0 + 8u * (2 * HS + 2 * BS + 8 + 2 * NB);
     volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - raw));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // see conv_gemm_kernel
+    const bool lead = elect_one();
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -568,13 +576,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *slot_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *slot_ptr, 0);
     pdl_launch_dependents();  // prologue done without touching global data: see conv_gemm_kernel
     pdl_wait();
 
     if (warp == 0) {
         // ===================== halo producer =====================
-        if (lane == 0) {
+        {
             int hs = 0;
             uint32_t hph = 0;
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -582,15 +590,17 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 halo_decode(p, item, nb, w0, h0, n);
                 for (int c = 0; c < p.cchunks; ++c) {
                     mbar_wait(h_empty(hs), hph ^ 1);
-                    mbar_expect_tx(h_full(hs), (uint32_t)Cfg::HALO_BYTES);
-                    tma_load_4d(sH0 + hs * Cfg::HALO_BYTES, &tmA, h_full(hs), c * 64, w0 - 1, h0 - 1, n);  // borders: zero fill
+                    if (lead) {
+                        mbar_expect_tx(h_full(hs), (uint32_t)Cfg::HALO_BYTES);
+                        tma_load_4d(sH0 + hs * Cfg::HALO_BYTES, &tmA, h_full(hs), c * 64, w0 - 1, h0 - 1, n);  // borders: zero fill
+                    }
                     if (++hs == HS) { hs = 0; hph ^= 1; }
                 }
             }
         }
     } else if (warp == 10) {
         // ===================== weight producer =====================
-        if (lane == 0) {
+        {
             int bs = 0;
             uint32_t bph = 0;
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -599,8 +609,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int c = 0; c < p.cchunks; ++c)
                     for (int t = 0; t < 9; ++t) {
                         mbar_wait(b_empty(bs), bph ^ 1);
-                        mbar_expect_tx(b_full(bs), (uint32_t)Cfg::B_BYTES);
-                        tma_load_2d(sB0 + bs * Cfg::B_BYTES, &tmB, b_full(bs), t * p.cin + c * 64, nb * BN);
+                        if (lead) {
+                            mbar_expect_tx(b_full(bs), (uint32_t)Cfg::B_BYTES);
+                            tma_load_2d(sB0 + bs * Cfg::B_BYTES, &tmB, b_full(bs), t * p.cin + c * 64, nb * BN);
+                        }
                         if (++bs == BS) { bs = 0; bph ^= 1; }
                     }
             }
@@ -624,7 +636,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int t = 0; t < 9; ++t) {
                     mbar_wait(b_full(bs), bph);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (lead) {
                         const int dy = t / 3, dx = t - dy * 3;
                         const uint32_t a0 = hbase + (uint32_t)(dy * 3072 + dx * 128 + half * 1024);  // right half: 8 pixels further
                         // start not 1024-aligned when dx != 0: the 128B-swizzle XOR is taken from the absolute smem
@@ -655,7 +667,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int q = warp & 3;
         const int m = q * 32 + lane;               // accumulator row = (row m / 8, pixel m % 8) of the half tile
         const int tg = (int)threadIdx.x - 64 - g * GT;
-        const bool T0 = tg == 0;
+        const bool T0 = ((warp - 2) & 3) == 0 && lead;
         const int barid = 1 + g;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const uint32_t ebuf_g = ebuf0 + (uint32_t)(g * NB) * Cfg::EPI_BUF;
