@@ -182,6 +182,10 @@ int skb_nms_batched_f32(const float* pred, int32_t b, int32_t n, int32_t nc, flo
 int skb_nms_batched_tiles_f32(const float* pred, int32_t b, int32_t n, int32_t nc, float conf_thr, float iou_thr, int32_t agnostic,
                               int32_t multi_label, int32_t max_det, int32_t compat, const int32_t* tile_xy_dev, float* out_packed,
                               int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
+/* Diagnostics only (no reference counterpart): counter_dev = device pointer of an unsigned 64-bit counter that receives the
+ * number of IoU pair tests of every following skb_nms_batched*_f32 call (SURVEY.md §8d asks for pairs/s on config 5;
+ * scripts/bench_nms_stress.py); NULL switches the counting kernel variant off. */
+int skb_debug_nms_pair_counter(unsigned long long* counter_dev);
 /* Gathered per-tile rows -> prediction tensor of the per-frame merge NMS.  gathered: fp32 [world][tiles_per_rank][max_det+1][7]
  * (rank r holds global tiles r, r + world, ...; global tile = frame * tiles_per_frame + k); pred: fp32
  * [n_frames][tiles_per_frame * max_det][5 + nc], fed to skb_nms_batched_f32 with the same compat. */

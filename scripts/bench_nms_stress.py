@@ -1,22 +1,32 @@
 """BASELINE config 5: dense small-object NMS stress -- pred [64, 50000, 15] fp32, 10 classes, unique
-objectness per image (tie-free cap).  Times the whole reference wrapper (filter -> cap 30 000 -> class-aware NMS ->
-max_det rows) as B200 kernels with CUDA events, checks 4 of the 64 images bit for bit against the CPU oracle, and times
-the oracle on those images beside it.  One JSON line on stdout."""
+objectness per image (tie-free cap) -- plus a clustered variant where suppression is really dense.
+
+Times the whole reference wrapper (filter -> cap 30 000 -> class-aware NMS -> max_det rows) as B200 kernels with CUDA events
+in BOTH compat modes, counts the IoU pair tests the kept-list kernel performs (skb_debug_nms_pair_counter) and reports pairs/s
+against the fp32 CUDA-core peak, and checks EVERY image bit for bit against the CPU oracle (C core, one host thread per
+image).  One JSON line on stdout."""
 import argparse
+import ctypes
 import json
 import os
 import sys
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "skyeye-aerial-object-detection-using-yolo_b200")]
+from skyeye import _native  # noqa: E402
 from skyeye.utils.nms import batched_nms_padded  # noqa: E402
 
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 148 SMs x 128 FMA lanes x 2 flop at clocks.max.sm
+FLOP_PER_PAIR = 21  # 2 max + 2 min + 2 sub + 2 max(0,.) + mul + add + sub + div (~8 on the FMA pipe) + compare, as torchvision evaluates it
 
-def make_pred(B, N, seed=0):
+
+def make_uniform(B, N, seed=0):
+    """uniform centres, log-uniform sizes: few overlaps."""
     g = np.random.default_rng(seed)
     p = np.empty((B, N, 15), dtype=np.float32)
     p[..., 0:2] = g.random((B, N, 2), dtype=np.float32) * 1280
@@ -28,44 +38,81 @@ def make_pred(B, N, seed=0):
     return p
 
 
+def make_clustered(B, N, seed=1, n_clusters=200):
+    """Same shape, but the candidates crowd around 200 object centres per image (a detector's real output on dense
+    small-object scenes): most candidates are suppressed, many 512-candidate chunks are walked."""
+    g = np.random.default_rng(seed)
+    p = np.empty((B, N, 15), dtype=np.float32)
+    centers = g.random((B, n_clusters, 2), dtype=np.float32) * 1200 + 40
+    which = g.integers(0, n_clusters, (B, N))
+    for b in range(B):
+        p[b, :, 0:2] = centers[b, which[b]] + g.normal(0, 2.0, (N, 2)).astype(np.float32)
+    p[..., 2:4] = (24 + g.random((B, N, 2), dtype=np.float32) * 8)
+    lin = np.linspace(0.002, 0.999, N).astype(np.float32)
+    for b in range(B):
+        p[b, :, 4] = g.permutation(lin)
+    p[..., 5:] = g.random((B, N, 10), dtype=np.float32) * 0.1
+    cls = g.integers(0, 10, (B, n_clusters))
+    for b in range(B):  # one dominant class per cluster
+        p[b, np.arange(N), 5 + cls[b, which[b]]] = 0.9 + g.random(N, dtype=np.float32) * 0.1
+    return p
+
+
+def run_case(pred, kw, iters, check, pool):
+    from oracle import nms as onms
+    L = _native.lib()
+    dev = torch.from_numpy(pred).cuda()
+    B, N = pred.shape[:2]
+    rows, cnt = batched_nms_padded(dev, **kw)
+    for _ in range(2):
+        batched_nms_padded(dev, out=rows, out_count=cnt, **kw)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):  # the 192 MB input is larger than L2: no flush needed
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        batched_nms_padded(dev, out=rows, out_count=cnt, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+    L.skb_debug_nms_pair_counter(ctypes.c_void_p(counter.data_ptr()))
+    batched_nms_padded(dev, out=rows, out_count=cnt, **kw)
+    torch.cuda.synchronize()
+    L.skb_debug_nms_pair_counter(None)
+    pairs = int(counter.item())
+    r = {"ms_per_batch": ms, "boxes_per_s": B * N / ms * 1e3, "input_gbs": pred.nbytes / ms / 1e6, "kept_total": int(cnt.sum().item()),
+         "iou_pair_tests": pairs, "pairs_per_s": pairs / ms * 1e3,
+         "fp32_frac_of_peak": pairs * FLOP_PER_PAIR / (ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS}
+    if check:
+        t0 = time.perf_counter()
+        ref = list(pool.map(lambda b: onms.non_max_suppression(pred[b:b + 1], **kw)[0], range(check)))
+        cpu_s = time.perf_counter() - t0
+        h_rows, h_cnt = rows.cpu().numpy(), cnt.cpu().numpy()
+        ok = [bool(h_cnt[b] == len(ref[b]) and np.array_equal(h_rows[b, :h_cnt[b], :ref[b].shape[1]], ref[b])) for b in range(check)]
+        r.update({"images_checked": check, "bit_exact_images": int(sum(ok)), "bit_exact": bool(all(ok)),
+                  "cpu_oracle_wall_s": cpu_s, "cpu_oracle_threads": pool._max_workers})
+    return r
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--n", type=int, default=50000)
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--check", type=int, default=4, help="images compared with the CPU oracle")
+    ap.add_argument("--check", type=int, default=64, help="images compared with the CPU oracle (all by default)")
     a = ap.parse_args()
-    pred = make_pred(a.batch, a.n)
-    dev = torch.from_numpy(pred).cuda()
-    res = {"workload": f"pred [{a.batch}, {a.n}, 15] fp32, 10 classes, seed 0", "input_mb": pred.nbytes / 1e6}
-    for name, kw in (("conf0.001_iou0.6", dict(conf_threshold=0.001, iou_threshold=0.6, multi_label=False)),
-                     ("conf0.25_iou0.45", dict(conf_threshold=0.25, iou_threshold=0.45, multi_label=False))):
-        rows, cnt = batched_nms_padded(dev, **kw)
-        for _ in range(2):
-            batched_nms_padded(dev, out=rows, out_count=cnt, **kw)
-        torch.cuda.synchronize()
-        ts = []
-        for _ in range(a.iters):  # the 192 MB input is larger than L2: no flush needed
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            batched_nms_padded(dev, out=rows, out_count=cnt, **kw)
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        ms = sorted(ts)[len(ts) // 2]
-        n_cand = int((pred[..., 4] > kw["conf_threshold"]).sum())
-        r = {"ms_per_batch": ms, "boxes_per_s": a.batch * a.n / ms * 1e3, "candidates_after_conf": n_cand,
-             "input_gbs": pred.nbytes / ms / 1e6, "kept_total": int(cnt.sum().item())}
-        if a.check:
-            from oracle import nms as onms
-            t0 = time.perf_counter()
-            ref = onms.non_max_suppression(pred[:a.check], **kw)
-            cpu_s = time.perf_counter() - t0
-            h_rows, h_cnt = rows.cpu().numpy(), cnt.cpu().numpy()
-            ok = all(h_cnt[b] == len(ref[b]) and np.array_equal(h_rows[b, :h_cnt[b], :ref[b].shape[1]], ref[b]) for b in range(a.check))
-            r.update({"bit_exact_images": a.check if ok else 0, "bit_exact": bool(ok), "cpu_oracle_boxes_per_s": a.check * a.n / cpu_s,
-                      "cpu_oracle_s_per_image": cpu_s / a.check})
-        res[name] = r
+    from oracle import nms as onms
+    onms.build()
+    pool = ThreadPoolExecutor(max_workers=os.cpu_count() or 1)
+    res = {"workload": f"pred [{a.batch}, {a.n}, 15] fp32, 10 classes", "fp32_peak_tflops": FP32_PEAK_TFLOPS, "flop_per_pair": FLOP_PER_PAIR}
+    check = min(a.check, a.batch)
+    for dname, pred in (("uniform", make_uniform(a.batch, a.n)), ("clustered", make_clustered(a.batch, a.n))):
+        for compat in ("reference", "fixed"):
+            for name, kw in (("conf0.001_iou0.6", dict(conf_threshold=0.001, iou_threshold=0.6, multi_label=False)),
+                             ("conf0.25_iou0.45", dict(conf_threshold=0.25, iou_threshold=0.45, multi_label=False))):
+                res[f"{dname}/{compat}/{name}"] = run_case(pred, dict(kw, compat=compat), a.iters, check, pool)
     print(json.dumps(res))
 
 

@@ -248,10 +248,15 @@ __device__ __forceinline__ void load_cand(const BatchedParams& p, int b, unsigne
     c.area = box_area(c.x1, c.y1, c.x2, c.y2);
 }
 
-// grid = B images, 256 threads. Sorted keys of image b are the segment [off_b, off_b + cnt_b).
+// Diagnostics (scripts/bench_nms_stress.py): when set, the COUNT variant of the kept-list kernel adds the number of IoU pair
+// tests it performed (phase A: candidate vs kept box; phase B1: survivor vs earlier survivor of the chunk) to this counter.
+static unsigned long long* g_nms_pair_counter = nullptr;
+
+// grid = B images, 512 threads. Sorted keys of image b are the segment [off_b, off_b + cnt_b).
+template <bool COUNT>
 __global__ void __launch_bounds__(NMS_THREADS)
 nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict__ keys, const int* __restrict__ count,
-                    float* __restrict__ out, int* __restrict__ out_count) {
+                    float* __restrict__ out, int* __restrict__ out_count, unsigned long long* __restrict__ pair_counter) {
     __shared__ float kx1[NMS_MAX_KEEP], ky1[NMS_MAX_KEEP], kx2[NMS_MAX_KEEP], ky2[NMS_MAX_KEEP], kar[NMS_MAX_KEEP];
     __shared__ int surv[NMS_THREADS];   // chunk-local ids of phase-A survivors, in order
     __shared__ int warp_cnt[NMS_THREADS / 32];
@@ -273,6 +278,7 @@ nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict_
     if (n > MAX_NMS_BOXES) n = MAX_NMS_BOXES;  // metrics.py:431-432 (sorted order => top-30000 by score)
     if (tid == 0) s_kept = 0;
     __syncthreads();
+    unsigned int n_pairs = 0;
 
     for (int base = 0; base < n; base += NMS_THREADS) {
         const int kept0 = s_kept;
@@ -283,8 +289,14 @@ nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict_
         if (alive) {
             load_cand(p, b, keys[off + i], c);
             // phase A: against everything kept in earlier chunks (parallel over candidates)
-            for (int k = 0; k < kept0; ++k)
-                if (iou_gt(kx1[k], ky1[k], kx2[k], ky2[k], kar[k], c.x1, c.y1, c.x2, c.y2, c.area, p.iou)) { alive = false; break; }
+            // (a zero intersection gives an overlap of 0 or NaN, never > thr for thr >= 0: the division is skipped for disjoint
+            // boxes, which is most of a dense scene's kept list -- 4.3 -> see profiles/r2c_nms_stress.md)
+            for (int k = 0; k < kept0; ++k) {
+                if (COUNT) ++n_pairs;
+                const float bx1 = kx1[k], by1 = ky1[k], bx2 = kx2[k], by2 = ky2[k];
+                if (fminf(bx2, c.x2) > fmaxf(bx1, c.x1) && fminf(by2, c.y2) > fmaxf(by1, c.y1) &&
+                    iou_gt(bx1, by1, bx2, by2, kar[k], c.x1, c.y1, c.x2, c.y2, c.area, p.iou)) { alive = false; break; }
+            }
         }
         // order-preserving compaction of survivors
         const unsigned int bal = __ballot_sync(0xffffffffu, alive);
@@ -312,6 +324,7 @@ nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict_
                 for (int w = 0; w <= (tid >> 5); ++w) {
                     const int j0 = w * 32, j1 = min(j0 + 32, tid);
                     unsigned int m = 0;
+                    if (COUNT) n_pairs += (unsigned int)(j1 - j0);
                     for (int j = j0; j < j1; ++j) {
                         const int u = surv[j];
                         const float xx1 = fmaxf(cx1[u], ax1), yy1 = fmaxf(cy1[u], ay1);
@@ -346,6 +359,11 @@ nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict_
         __syncthreads();
     }
     if (tid == 0) out_count[b] = s_kept;
+    if (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_pairs += __shfl_xor_sync(0xffffffffu, n_pairs, o);
+        if (lane == 0 && pair_counter) atomicAdd(pair_counter, (unsigned long long)n_pairs);
+    }
     if (p.out_rows > p.max_det) {  // gather-buffer form: zero the unused rows, append the count row
         const int kept = s_kept;
         for (int i = kept * 7 + tid; i < p.out_rows * 7; i += NMS_THREADS) out_b[i] = i == p.max_det * 7 ? (float)kept : 0.0f;
@@ -410,6 +428,13 @@ extern "C" int skb_nms_f32(const float* boxes, const float* scores, int32_t n, f
     return SKB_OK;
 }
 
+// Diagnostics: device pointer of an unsigned 64-bit counter that receives the IoU pair tests of every following batched NMS
+// call (NULL switches the counting variant off again).
+extern "C" int skb_debug_nms_pair_counter(unsigned long long* counter_dev) {
+    g_nms_pair_counter = counter_dev;
+    return SKB_OK;
+}
+
 extern "C" size_t skb_nms_batched_workspace_bytes(int32_t b, int32_t n, int32_t nc, int32_t multi_label) {
     if (b <= 0 || n <= 0) return 256;
     return batched_layout(b, n, nc, multi_label, nullptr, nullptr);
@@ -443,6 +468,8 @@ static int nms_batched_impl(const float* pred, int32_t b, int32_t n, int32_t nc,
     if (rc != SKB_OK) return rc;
     SKB_REQUIRE(pred && out && out_count && workspace && b > 0 && n > 0 && nc >= 0, SKB_ERR_ARG, "nms_batched: bad arguments");
     SKB_REQUIRE(compat == 0 || compat == 1, SKB_ERR_ARG, "nms_batched: compat must be 0 (reference) or 1 (fixed)");
+    SKB_REQUIRE(iou_thr >= 0.0f && iou_thr <= 1.0f && conf_thr >= 0.0f && conf_thr <= 1.0f, SKB_ERR_ARG,
+                "nms_batched: thresholds must lie in [0, 1] (metrics.py:386-387), got conf %g iou %g", (double)conf_thr, (double)iou_thr);
     SKB_REQUIRE(max_det >= 1 && max_det <= NMS_MAX_KEEP, SKB_ERR_UNSUPPORTED, "nms_batched: max_det=%d (supported: 1..%d)", max_det, NMS_MAX_KEEP);
     int slot_bits = 1, img_bits = 1;
     while ((1L << slot_bits) < (long)n * (nc > 1 ? nc : 1)) ++slot_bits;
@@ -476,8 +503,12 @@ static int nms_batched_impl(const float* pred, int32_t b, int32_t n, int32_t nc,
     bp.tile_xy = tile_xy_dev; bp.out_rows = out_rows;
     constexpr int kMaskBytes = NMS_THREADS * (NMS_THREADS / 32) * (int)sizeof(unsigned int);
     static PerDeviceOnce attr_once;
-    if (attr_once.first()) SKB_CUDA(cudaFuncSetAttribute(nms_keptlist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaskBytes));
-    nms_keptlist_kernel<<<b, NMS_THREADS, kMaskBytes, st>>>(bp, ws.keys_out, ws.count, out, out_count);
+    if (attr_once.first()) {
+        SKB_CUDA(cudaFuncSetAttribute(nms_keptlist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaskBytes));
+        SKB_CUDA(cudaFuncSetAttribute(nms_keptlist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaskBytes));
+    }
+    if (g_nms_pair_counter) nms_keptlist_kernel<true><<<b, NMS_THREADS, kMaskBytes, st>>>(bp, ws.keys_out, ws.count, out, out_count, g_nms_pair_counter);
+    else nms_keptlist_kernel<false><<<b, NMS_THREADS, kMaskBytes, st>>>(bp, ws.keys_out, ws.count, out, out_count, nullptr);
     SKB_LAUNCH_CHECK();
     return SKB_OK;
 }
