@@ -89,10 +89,24 @@ def workload_config(variant, size, batch):
             "sharding": f"images by rank, {batch} per GPU, no data-path collective"}
 
 
-def cpu_oracle_run(variant, size, n_images, steps, warmup, seed=1234, sd=None, cfg=None):
-    """Times the oracle port (oracle/model.py + oracle/nms.py: the reference's PyTorch fp32 path and
-    torchvision-style NMS restated) on this box's host cores.
-    Returns (images/s, cores, seconds/step, (det, raws, nms_rows) of the last pass)."""
+def cpu_reference_kind():
+    """"reference" when the reference's own files are reachable (the build container's /root/reference, or the copy build()
+    staged under the git-ignored oracle/_ref/ for the GPU box), else "port" (oracle/model.py + oracle/nms.py)."""
+    if os.environ.get("SKYEYE_CPU_ARM") == "port":
+        return "port"
+    try:
+        from oracle import ref_loader
+        return "reference" if ref_loader.available() else "port"
+    except Exception:
+        return "port"
+
+
+def cpu_oracle_run(variant, size, n_images, steps, warmup, seed=1234, sd=None, cfg=None, kind=None):
+    """Times the reference path on this box's host cores: kind "reference" = the reference's OWN modules (detector.py,
+    backbone.py, blocks.py, attention.py incl. nn.MultiheadAttention materialising the N x N weights, metrics.py's
+    non_max_suppression over torchvision.ops.nms) with the enumerated repairs R1-R4 of SURVEY.md §0.2; kind "port" = the
+    restatement under oracle/ (same arithmetic, attention evaluated in chunks).
+    Returns (images/s, cores, seconds/step, (det, raws, nms_rows) of the last pass, kind)."""
     import torch
     from oracle import model as om
     from oracle import nms as onms
@@ -100,20 +114,33 @@ def cpu_oracle_run(variant, size, n_images, steps, warmup, seed=1234, sd=None, c
     torch.set_num_threads(cores)
     if sd is None:
         sd, cfg = shared_state_dict(variant)
+    kind = kind or cpu_reference_kind()
     x = torch.from_numpy(synthetic_images(n_images, size, seed)).float() / 255.0
-    onms.build()
+    ref_model = ref_nms = None
+    if kind == "reference":
+        from oracle import ref_loader
+        ref_model = ref_loader.build_reference_model(cfg)
+        missing = ref_model.load_state_dict(sd, strict=True)
+        ref_nms = ref_loader.load().metrics.non_max_suppression
+    else:
+        onms.build()
     ts = []
     last = None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        det, raws = om.forward(x, sd, cfg)
-        rows = onms.non_max_suppression(det.numpy(), CONF, IOU, max_detections=MAX_DET)
+        if ref_model is not None:
+            with torch.no_grad():
+                det, raws = ref_model(x)
+                rows = [r.numpy() for r in ref_nms(det, CONF, IOU, max_detections=MAX_DET)]
+        else:
+            det, raws = om.forward(x, sd, cfg)
+            rows = onms.non_max_suppression(det.numpy(), CONF, IOU, max_detections=MAX_DET)
         dt = time.perf_counter() - t0
         last = (det, raws, rows)
         if i >= warmup:
             ts.append(dt)
     total = sum(ts)
-    return n_images * len(ts) / total, cores, total / len(ts), last
+    return n_images * len(ts) / total, cores, total / len(ts), last, kind
 
 
 def run_reference(args):
@@ -121,15 +148,18 @@ def run_reference(args):
     if rank != 0:
         return
     n_img = 1  # bounded sample: one image of the 16-image batch per step
-    value, cores, sec, _ = cpu_oracle_run(args.variant, args.size, n_img, args.steps, args.warmup)
+    value, cores, sec, _, kind = cpu_oracle_run(args.variant, args.size, n_img, args.steps, args.warmup)
     sample = f"{n_img} image of the {args.batch}-image batch per step, {args.variant} {args.size}x{args.size} fp32, forward+decode+NMS"
+    arm = ("the reference's own PyTorch modules (oracle/_ref: detector/backbone/blocks/attention.py + metrics.non_max_suppression over "
+           "torchvision.ops.nms, repairs R1-R4), fp32, eager, all host cores" if kind == "reference"
+           else "CPU oracle port of the reference path (fp32, PyTorch eager + C NMS)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.variant, args.size, args.batch),
-        "run": {"arm": "CPU oracle port of the reference path (fp32, PyTorch eager + C NMS)", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "run": {"arm": arm, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -445,9 +475,12 @@ def run_b200(args):
         g_raws = [r[0].float().cpu() for r in plan.raw_out]
         g_det0 = plan.det[:1].float().cpu()
         g_rows = nms_out[0, :int(nms_cnt[0])].cpu().numpy()
-        v, cores, sec, (o_det, o_raws, o_rows) = cpu_oracle_run(args.variant, S, 1, 1, 1, seed=1234 + rank, sd=sd, cfg=ocfg)
-        cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"1 image of the {B}-image batch (1 warm-up + 1 timed pass, {sec:.1f} s), {args.variant} {S}x{S} fp32 oracle forward+decode+NMS"}
+        v, cores, sec, (o_det, o_raws, o_rows), ckind = cpu_oracle_run(args.variant, S, 1, 1, 1, seed=1234 + rank, sd=sd, cfg=ocfg)
+        o_raws = [r.detach() for r in o_raws]
+        o_det = o_det.detach()
+        cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": ckind,
+               "sample": f"1 image of the {B}-image batch (1 warm-up + 1 timed pass, {sec:.1f} s), {args.variant} {S}x{S} fp32 "
+                         f"{'reference modules' if ckind == 'reference' else 'oracle port'} forward+decode+NMS"}
         import numpy as np
         from oracle import nms as onms
         lv = []
@@ -456,7 +489,7 @@ def run_b200(args):
             lv.append({"max_rel": float((a - b).abs().max() / b.abs().max()), "rms": float((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt())})
         ref_rows = onms.non_max_suppression(g_det0.numpy(), CONF, IOU, max_detections=MAX_DET)[0]   # oracle NMS on the GPU's own detections
         dec = ((g_det0[..., 4:] > 0.5) == (o_det[..., 4:] > 0.5)).float().mean()
-        parity = {"vs": "fp32 CPU oracle, image 0 of the batch, same state dict", "max_rel": max(l["max_rel"] for l in lv),
+        parity = {"vs": f"fp32 CPU {'reference modules' if ckind == 'reference' else 'oracle port'}, image 0 of the batch, same state dict", "max_rel": max(l["max_rel"] for l in lv),
                   "rms": max(l["rms"] for l in lv), "per_level": lv,
                   "nms_rows_equal": bool(g_rows.shape == ref_rows.shape and np.array_equal(g_rows, ref_rows)),
                   "nms_rows": int(g_rows.shape[0]), "sigmoid_decisions_agree": float(dec),

@@ -1,10 +1,12 @@
 """Import the UNMODIFIED reference (``/root/reference``) under the alias package
 ``skyeye_ref`` and apply the enumerated repairs R1-R4 + (inj) of SURVEY.md §0.2.
 
-Only usable in the build container (the GPU box has no ``/root/reference``).
-Used by ``tests/golden/make_golden.py`` to generate the committed fixtures and
-by the ``reference``-marked CPU tests that pin the oracle to the reference.
-Nothing here copies reference source: modules are imported from where they lie.
+Used by ``tests/golden/make_golden.py`` to generate the committed fixtures, by the
+``reference``-marked CPU tests that pin the oracle to the reference, and by ``bench.py``'s CPU
+legs.  In the build container the modules are imported from where they lie
+(``/root/reference``); the GPU box has no such directory, so ``__graft_entry__.build()`` stages
+the five files of the path under the git-ignored ``oracle/_ref/`` (``stage_for_gpu_box``), which
+travels with the snapshot like the built ``.so`` files and never enters history.
 """
 from __future__ import annotations
 
@@ -14,12 +16,47 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("SKYEYE_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REF_COPY = os.path.join(_HERE, "_ref")  # git-ignored, NOT gpurun-ignored: travels to the GPU box like the built .so files
+# The five files the path executes: the detector, its blocks / backbone / attention modules and the NMS wrapper.
+REF_FILES = ("skyeye/core/models/detector.py", "skyeye/core/models/backbone.py", "skyeye/core/models/blocks.py",
+             "skyeye/core/models/attention.py", "skyeye/utils/metrics.py")
 ALIAS = "skyeye_ref"
 
 
+def _has(root: str) -> bool:
+    return all(os.path.isfile(os.path.join(root, f)) for f in REF_FILES)
+
+
+def _resolve_root() -> str:
+    env = os.environ.get("SKYEYE_REFERENCE_ROOT")
+    if env:
+        return env
+    return "/root/reference" if _has("/root/reference") else _REF_COPY
+
+
+REF_ROOT = _resolve_root()
+
+
 def available() -> bool:
-    return os.path.isfile(os.path.join(REF_ROOT, "skyeye", "core", "models", "detector.py"))
+    return _has(REF_ROOT)
+
+
+def stage_for_gpu_box(src: str = "/root/reference") -> str:
+    """Build step (``__graft_entry__.build``), build container only: place the UNMODIFIED reference files of the path under the
+    git-ignored ``oracle/_ref/`` so that ``bench.py --impl reference`` and the ``cpu_baseline`` leg can time the reference's own
+    PyTorch code on the GPU box's host cores (``kind = "reference"``), where ``/root/reference`` does not exist.  Nothing is
+    committed: ``oracle/_ref/`` is listed in ``.gitignore`` and the files never enter history."""
+    import filecmp
+    import shutil
+    if not _has(src):
+        return _REF_COPY if _has(_REF_COPY) else ""
+    for f in REF_FILES:
+        dst = os.path.join(_REF_COPY, f)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if not (os.path.isfile(dst) and filecmp.cmp(os.path.join(src, f), dst, shallow=False)):
+            shutil.copyfile(os.path.join(src, f), dst)
+    return _REF_COPY
 
 
 def _pkg(name: str, path: str) -> types.ModuleType:
@@ -49,6 +86,12 @@ def load():
                 importlib.import_module(stub)
             except Exception:
                 sys.modules[stub] = types.ModuleType(stub)
+    if not os.path.isfile(os.path.join(base, "utils", "general.py")) and ALIAS + ".utils.general" not in sys.modules:
+        # (inj) staged copy (oracle/_ref): metrics.py:14 only takes LOGGER from utils/general.py, which is not on the path
+        import logging
+        g = types.ModuleType(ALIAS + ".utils.general")
+        g.LOGGER = logging.getLogger("skyeye")
+        sys.modules[ALIAS + ".utils.general"] = g
     import torch
     import torch.nn as nn
     import torchvision
