@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch the forward plan kernel by kernel instead of replaying its CUDA graph")
     ap.add_argument("--no-tiled", action="store_true", help="skip the config-4 leg (16 4K frames = 128 tiles, tile-sharded, gather + merge)")
     ap.add_argument("--tiled-steps", type=int, default=0, help="timed steps of the config-4 leg (default: 4 at N=1, --steps otherwise)")
+    ap.add_argument("--no-variants", action="store_true", help="skip the informational skyeye_lw (windowed heads) leg")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel table here")
     return ap.parse_args()
 
@@ -462,6 +463,34 @@ def run_b200(args):
                            "every rank; gather + merge of step t on a second stream under the forward of step t+1; frames resident"}
         del td, frames
 
+    # Informational (beside -- not instead of -- the headline): the same network with `head: windowed`
+    # (WindowedSelfAttention over 8x8 windows, O(N w^2) instead of O(N^2)); same backbone / neck weights, its own head weights.
+    windowed = None
+    if world == 1 and not args.no_variants and args.variant == VARIANT and S == H:
+        sdw, _ = shared_state_dict("skyeye_lw")
+        mw = construct_model("skyeye_lw.yaml")
+        mw.load_state_dict(sdw, strict=True)
+        mw = mw.to(dev).eval()
+
+        def step_w():
+            dw, _ = mw(x_dev)
+            batched_nms_padded(dw, CONF, IOU, max_detections=MAX_DET, out=nms_out, out_count=nms_cnt)
+
+        for _ in range(3):
+            step_w()
+        wsteps = min(args.steps, 5)
+        ms_w = timed(step_w, wsteps) / wsteps
+        pw = mw.plan_for(x_dev)
+        mw._img[0] = x_dev
+        rows_w = pw.run_timed()
+        att_w = sum(ms for (nm, ms), meta in zip(rows_w, pw.meta) if meta["kind"] == "attention")
+        att_g = table["attention"]["ms_per_step"]
+        windowed = {"variant": "skyeye_lw (head: windowed, window_size 8)", "images_per_s": B / (ms_w / 1e3), "ms_per_step": ms_w,
+                    "attention_ms_per_step": att_w, "global_attention_ms_per_step": att_g,
+                    "note": "window attention core = skb_window_attn2d_bf16 (CUDA-core kernel, one CTA per window and head); "
+                            "detections differ from skyeye_l by construction (a different head)"}
+        del mw, pw
+
     launches_per_step = plan.launches + NMS_LAUNCHES
     from skyeye.engine import View
     act_gb = sum(v.t.numel() * v.t.element_size() for v in plan.keep if isinstance(v, View)) / 1e9
@@ -514,6 +543,7 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "parity": parity,
             "tiled4k": tiled,
+            "windowed_head": windowed,
             "latency_b1": latency,
             "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in table.items()},
         }

@@ -146,6 +146,13 @@ int skb_debug_attn_prof(unsigned long long* out16, int32_t reset);
  * head_dim = C / heads must be a multiple of 8 and <= 64. */
 int skb_window_attn_bf16(const skb_view* qkv, const float* bias, const float* mask, int32_t n_mask, const skb_view* o,
                          int32_t heads, float scale, void* stream);
+/* The same core with window partition and reverse folded into its addressing (NOT IN REFERENCE: the class is never wired,
+ * SURVEY.md X5 / §8f N3; Swin-style partition of attention.py:358's input layout): qkv bf16 view [B,H,W,3C] and o bf16 view
+ * [B,H,W,C] are unpartitioned feature maps, H and W multiples of `window` (<= 8); window w of an image (row-major over the
+ * window grid) covers pixels (wy*window .., wx*window ..), token t of it is pixel (t / window, t % window) of that square;
+ * mask [n_mask, w*w, w*w] is indexed by (window index within the image) % n_mask. */
+int skb_window_attn2d_bf16(const skb_view* qkv, const float* bias, const float* mask, int32_t n_mask, const skb_view* o,
+                           int32_t heads, int32_t window, float scale, void* stream);
 
 /* ---- decode (DetectionHead.process_detections, detector.py:88-145) -----------------------------
  * raw[l]: fp32 view [B,h_l,w_l,>=na*no] (channel = a*no + o, the 1x1 head conv output); 16-byte aligned,

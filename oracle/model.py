@@ -43,6 +43,10 @@ VARIANTS = {
     "skyeye_tiny_l": dict(base_channels=8, depth_multiple=0.33, nc=10, enhanced=True, head_dim=16),
     # smallest variant whose every channel count is a multiple of 32 (tcgen05 path test size)
     "skyeye_nano_l": dict(base_channels=32, depth_multiple=0.33, nc=10, enhanced=True, head_dim=64),
+    # head: windowed (NOT IN REFERENCE): the global attention of the D4 heads replaced by the reference's
+    # WindowedSelfAttention class (attention.py:312-399) over window_size x window_size windows
+    "skyeye_nano_lw": dict(base_channels=32, depth_multiple=0.33, nc=10, enhanced=True, head_dim=64, head="windowed", window_size=8),
+    "skyeye_lw": dict(base_channels=64, depth_multiple=1.0, nc=10, enhanced=True, head_dim=64, head="windowed", window_size=8),
 }
 
 
@@ -52,6 +56,8 @@ def get_cfg(variant) -> dict:
     cfg.setdefault("enhanced", False)
     cfg.setdefault("head_dim", 64)
     cfg.setdefault("anchors", None)
+    cfg.setdefault("head", "transformer" if cfg["enhanced"] else "conv")  # D4: the enhanced variants carry transformer heads
+    cfg.setdefault("window_size", 8)
     return cfg
 
 
@@ -131,12 +137,21 @@ def state_spec(cfg) -> List[Tuple[str, tuple, tuple]]:
                                  ("value_projection", ck, ck), ("output_projection", cq, ck)):
                 spec.append((f"{name}.{proj}.weight", (co, ci, 1, 1), ("normal", 1.0 / math.sqrt(ci))))
                 spec.append((f"{name}.{proj}.bias", (co,), ("normal", 0.1)))
-        for i, c in enumerate((c3, c4, c5)):  # D4: TransformerLayer per level (attention.py:244-309)
+        for i, c in enumerate((c3, c4, c5) if cfg["head"] != "conv" else ()):  # D4: TransformerLayer per level (attention.py:244-309)
             p = f"head_transformers.{i}"
-            spec.append((p + ".self_attn.in_proj_weight", (3 * c, c), ("normal", 1.0 / math.sqrt(c))))
-            spec.append((p + ".self_attn.in_proj_bias", (3 * c,), ("normal", 0.02)))
-            spec.append((p + ".self_attn.out_proj.weight", (c, c), ("normal", 1.0 / math.sqrt(c))))
-            spec.append((p + ".self_attn.out_proj.bias", (c,), ("normal", 0.02)))
+            if cfg["head"] == "windowed":  # WindowedSelfAttention parameters + buffer (attention.py:333-353) in registration order
+                ws, nh = cfg["window_size"], max(c // cfg["head_dim"], 1)
+                spec.append((p + ".attn.relative_position_bias_table", ((2 * ws - 1) ** 2, nh), ("normal", 0.02)))
+                spec.append((p + ".attn.relative_position_index", (ws * ws, ws * ws), ("relidx", ws)))
+                spec.append((p + ".attn.qkv.weight", (3 * c, c), ("normal", 1.0 / math.sqrt(c))))
+                spec.append((p + ".attn.qkv.bias", (3 * c,), ("normal", 0.02)))
+                spec.append((p + ".attn.proj.weight", (c, c), ("normal", 1.0 / math.sqrt(c))))
+                spec.append((p + ".attn.proj.bias", (c,), ("normal", 0.02)))
+            else:
+                spec.append((p + ".self_attn.in_proj_weight", (3 * c, c), ("normal", 1.0 / math.sqrt(c))))
+                spec.append((p + ".self_attn.in_proj_bias", (3 * c,), ("normal", 0.02)))
+                spec.append((p + ".self_attn.out_proj.weight", (c, c), ("normal", 1.0 / math.sqrt(c))))
+                spec.append((p + ".self_attn.out_proj.bias", (c,), ("normal", 0.02)))
             spec.append((p + ".norm1.weight", (c,), ("normal1", 0.1)))
             spec.append((p + ".norm1.bias", (c,), ("normal", 0.1)))
             spec.append((p + ".norm2.weight", (c,), ("normal1", 0.1)))
@@ -162,6 +177,9 @@ def make_state_dict(cfg, seed: int = 0, trained_like: bool = True) -> SD:
         rng = np.random.Generator(np.random.PCG64([seed, zlib.crc32(key.encode())]))
         if kind == "int":
             sd[key] = torch.tensor(int(arg), dtype=torch.long)
+            continue
+        if kind == "relidx":  # registered buffer of WindowedSelfAttention (attention.py:340-352)
+            sd[key] = relative_position_index(int(arg))
             continue
         if kind == "conv":
             a = rng.standard_normal(shape, dtype=np.float32) * math.sqrt(2.0 / arg)
@@ -446,6 +464,50 @@ def windowed_self_attention(x, sd, p, window, heads, mask=None, ctx=FP32) -> Ten
     return ctx.q(F.linear(o, wp, sd[p + ".proj.bias"]))
 
 
+def window_partition(t: Tensor, window: int) -> Tensor:
+    """[B, H, W, C] -> [B * nW, window * window, C]: the input layout WindowedSelfAttention.forward documents
+    (attention.py:358-365); windows row-major over the window grid, tokens row-major inside a window.  NOT IN REFERENCE
+    (the class is never wired): the standard Swin partition."""
+    B, H, W, C = t.shape
+    t = t.view(B, H // window, window, W // window, window, C)
+    return t.permute(0, 1, 3, 2, 4, 5).reshape(-1, window * window, C)
+
+
+def window_reverse(wins: Tensor, window: int, H: int, W: int) -> Tensor:
+    """Inverse of ``window_partition``: [B * nW, window * window, C] -> [B, H, W, C]."""
+    B = wins.shape[0] // ((H // window) * (W // window))
+    t = wins.view(B, H // window, W // window, window, window, -1)
+    return t.permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, -1)
+
+
+def windowed_transformer_layer(x, sd, p, heads, window, ctx=FP32) -> Tensor:
+    """``head: windowed`` (NOT IN REFERENCE): TransformerLayer.forward (attention.py:282-309) with
+    ``self_attn`` replaced by WindowedSelfAttention (attention.py:358-399) over non-overlapping windows:
+    t + reverse(attn(partition(norm1(t)))), then t + feedforward(norm2(t)).  Stored points as in ``transformer_layer``."""
+    B, C, H, W = x.shape
+    hd = C // heads
+    wr = (lambda t: bf16_round(t)) if ctx.emu else (lambda t: t)
+    tap = lambda sfx, z: ctx.tap(p + sfx, z.transpose(1, 2).reshape(B, z.shape[-1], H, W)) is None or z  # tokens -> NCHW
+    t = x.flatten(2).transpose(1, 2)  # [B, N, C]
+    xn = tap(".ln1", ctx.q(F.layer_norm(t, (C,), sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], 1e-5)))
+    a = p + ".attn"
+    qkv = tap(".qkv", ctx.q(F.linear(xn, wr(sd[a + ".qkv.weight"]), sd[a + ".qkv.bias"])))          # per token: order-free
+    n_tok = window * window
+    qw = window_partition(qkv.view(B, H, W, 3 * C), window)                                             # [B*nW, n_tok, 3C]
+    qw = qw.reshape(-1, n_tok, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = qw[0] * (hd ** -0.5), qw[1], qw[2]
+    attn = q @ k.transpose(-2, -1)
+    bias = sd[a + ".relative_position_bias_table"][relative_position_index(window).view(-1)].view(n_tok, n_tok, heads)
+    attn = attn + bias.permute(2, 0, 1).unsqueeze(0)
+    o = (torch.softmax(attn, dim=-1) @ v).transpose(1, 2).reshape(-1, n_tok, C)
+    o = tap(".attn", ctx.q(window_reverse(o, window, H, W).reshape(B, H * W, C)))
+    t = tap(".proj", ctx.q(t + F.linear(o, wr(sd[a + ".proj.weight"]), sd[a + ".proj.bias"])))
+    xn = tap(".ln2", ctx.q(F.layer_norm(t, (C,), sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], 1e-5)))
+    h = tap(".ff0", ctx.q(F.relu(F.linear(xn, wr(sd[p + ".feedforward.0.weight"]), sd[p + ".feedforward.0.bias"]))))
+    t = tap(".ff3", ctx.q(t + F.linear(h, wr(sd[p + ".feedforward.3.weight"]), sd[p + ".feedforward.3.bias"])))
+    return t.transpose(1, 2).reshape(B, C, H, W)
+
+
 def features(x, sd, cfg, ctx=FP32) -> List[Tensor]:
     """Everything before the detection head: [p3, p4, p5] level features."""
     cfg = get_cfg(cfg)
@@ -456,7 +518,13 @@ def features(x, sd, cfg, ctx=FP32) -> List[Tensor]:
         hd = cfg["head_dim"]
         lv = []
         for i, f in enumerate((p3, p4, p5)):
-            lv.append(transformer_layer(f, sd, f"head_transformers.{i}", max(f.shape[1] // hd, 1), ctx))
+            nh = max(f.shape[1] // hd, 1)
+            if cfg["head"] == "windowed":
+                lv.append(windowed_transformer_layer(f, sd, f"head_transformers.{i}", nh, cfg["window_size"], ctx))
+            elif cfg["head"] == "transformer":
+                lv.append(transformer_layer(f, sd, f"head_transformers.{i}", nh, ctx))
+            else:
+                lv.append(f)
         p3, p4, p5 = lv
     return [p3, p4, p5]
 
@@ -486,7 +554,9 @@ def calibrate_bn(sd: SD, cfg, x: Tensor) -> SD:
     cfg = get_cfg(cfg)
     out = dict(sd)
     ctx = Ctx(None, None, calib=True)
-    head(features(x.float(), out, cfg, ctx), out, cfg["nc"], ctx)
+    # every BatchNorm sits in the backbone / neck, upstream of the per-level heads: the heads need not run (and the windowed
+    # heads could not, on a calibration image whose level maps are not multiples of the window)
+    features(x.float(), out, dict(cfg, head="conv"), ctx)
     return out
 
 

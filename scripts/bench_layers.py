@@ -104,6 +104,29 @@ def main():
         ms = sorted(ts)[len(ts) // 2]
         res[name] = dict(ms=ms, tflops=fl / ms / 1e9)
         print(f"{name:22s} {ms:8.3f} ms {fl / ms / 1e9:8.1f} TF/s", flush=True)
+    # head: windowed: the per-window attention core on the unpartitioned qkv map, window 8, head_dim 64
+    for name, (B, H, W, heads) in {"wattn_p3": (16, 160, 160, 4), "wattn_p4": (16, 80, 80, 8), "wattn_p5": (16, 40, 40, 16)}.items():
+        if sel and name not in sel:
+            continue
+        C = heads * 64
+        qkv = E.View(torch.randn((B, H, W, 3 * C), device="cuda").to(torch.bfloat16))
+        o = E.new_buffer(B, H, W, C)
+        bias = torch.randn((heads, 64, 64), device="cuda") * 0.02
+        for _ in range(2):
+            E.window_attn2d(qkv, bias, None, o, heads, 8, 0.125)
+        ts = []
+        for _ in range(a.iters):
+            flush_l2(flush)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            E.window_attn2d(qkv, bias, None, o, heads, 8, 0.125)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[len(ts) // 2]
+        by = 2.0 * (qkv.t.numel() + o.t.numel())
+        res[name] = dict(ms=ms, tflops=4.0 * B * H * W * 64 * C / ms / 1e9, gbs=by / ms / 1e6)
+        print(f"{name:22s} {ms:8.3f} ms {res[name]['tflops']:8.1f} TF/s {by / ms / 1e6:8.0f} GB/s", flush=True)
     if a.json:
         json.dump(res, open(a.json, "w"), indent=1)
 

@@ -510,34 +510,50 @@ extern "C" int skb_debug_attn_prof(unsigned long long* out16, int32_t reset) {
 // additive window mask.  One CTA per (window, head), one thread per query row; K and V of the window live in
 // shared memory as bf16 and every thread walks them with broadcast reads.  4*N^2*d flop per window-head is tiny
 // (N <= 64): the kernel is bound by reading qkv and writing o once, so no tensor-core path is needed here.
+// Two addressing modes: ws == 0, the reference class's own layout (x [B*nW, w*w, C]: window `win` is a contiguous run of
+// N tokens); ws > 0, window partition and reverse folded into the addressing (NOT IN REFERENCE): qkv and
+// o are feature maps [B, H, W, .], window `win` of image n covers pixels (wy*ws .. +ws, wx*ws .. +ws) and token t of it
+// is pixel (wy*ws + t / ws, wx*ws + t % ws) -- the per-token qkv / proj GEMMs run on the unpartitioned map and no
+// partitioned copy ever exists.
 // =============================================================================================
 namespace skb {
 
 template <int HD>
 __global__ void __launch_bounds__(64)
 window_attn_kernel(const __nv_bfloat16* __restrict__ qkv, long qpitch, const float* __restrict__ bias, const float* __restrict__ mask,
-                   int n_mask, __nv_bfloat16* __restrict__ out, long opitch, int N, int C, float scale) {
+                   int n_mask, __nv_bfloat16* __restrict__ out, long opitch, int N, int C, float scale, int ws, int Wimg, int wins_x,
+                   int wins_per_img) {
     __shared__ __align__(16) __nv_bfloat16 sK[64 * HD];
     __shared__ __align__(16) __nv_bfloat16 sV[64 * HD];
     const int win = blockIdx.x, head = blockIdx.y, t = threadIdx.x;
-    const __nv_bfloat16* base = qkv + (long)win * N * qpitch + head * HD;
+    // token index of the window -> token (pixel) index of the tensor
+    long tok0 = (long)win * N;
+    if (ws > 0) {
+        const int n = win / wins_per_img, w = win - n * wins_per_img;
+        const int wy = w / wins_x, wx = w - wy * wins_x;
+        tok0 = ((long)n * (wins_per_img / wins_x) * ws + (long)wy * ws) * Wimg + (long)wx * ws;  // pixel (n, wy*ws, wx*ws)
+    }
+    auto tok = [&](int r) { return ws > 0 ? tok0 + (long)(r / ws) * Wimg + (r % ws) : tok0 + r; };
+    const __nv_bfloat16* base = qkv + head * HD;
     for (int i = t; i < N * (HD / 8); i += 64) {  // 16-byte pieces of the K and V rows of this head
         const int r = i / (HD / 8), c = i - r * (HD / 8);
-        reinterpret_cast<uint4*>(sK)[i] = *reinterpret_cast<const uint4*>(base + (long)r * qpitch + C + c * 8);
-        reinterpret_cast<uint4*>(sV)[i] = *reinterpret_cast<const uint4*>(base + (long)r * qpitch + 2 * C + c * 8);
+        const __nv_bfloat16* rowp = base + tok(r) * qpitch;
+        reinterpret_cast<uint4*>(sK)[i] = *reinterpret_cast<const uint4*>(rowp + C + c * 8);
+        reinterpret_cast<uint4*>(sV)[i] = *reinterpret_cast<const uint4*>(rowp + 2 * C + c * 8);
     }
     __syncthreads();
     if (t >= N) return;
+    base += tok(t) * qpitch;  // this thread's query row
     float q[HD];
 #pragma unroll
     for (int c = 0; c < HD / 8; ++c) {
-        const uint4 u = *reinterpret_cast<const uint4*>(base + (long)t * qpitch + c * 8);
+        const uint4 u = *reinterpret_cast<const uint4*>(base + c * 8);
         const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) { q[c * 8 + 2 * k] = bf16_lo(w4[k]) * scale; q[c * 8 + 2 * k + 1] = bf16_hi(w4[k]) * scale; }
     }
     const float* brow = bias + ((long)head * N + t) * N;
-    const float* mrow = mask ? mask + ((long)(win % n_mask) * N + t) * N : nullptr;
+    const float* mrow = mask ? mask + ((long)((ws > 0 ? win % wins_per_img : win) % n_mask) * N + t) * N : nullptr;
     float s[64];
     float mx = -INFINITY;
 #pragma unroll
@@ -581,7 +597,7 @@ window_attn_kernel(const __nv_bfloat16* __restrict__ qkv, long qpitch, const flo
         }
     }
     const float inv = 1.0f / l;
-    __nv_bfloat16* dst = out + ((long)win * N + t) * opitch + head * HD;
+    __nv_bfloat16* dst = out + tok(t) * opitch + head * HD;
 #pragma unroll
     for (int c = 0; c < HD / 8; ++c) {
         uint4 u;
@@ -612,9 +628,36 @@ extern "C" int skb_window_attn_bf16(const skb_view* qkv, const float* bias, cons
     cudaStream_t st = (cudaStream_t)stream;
     const __nv_bfloat16* qp = (const __nv_bfloat16*)qkv->ptr;
     __nv_bfloat16* op = (__nv_bfloat16*)o->ptr;
-    if (hd == 64) window_attn_kernel<64><<<grid, 64, 0, st>>>(qp, qkv->pitch, bias, mask, n_mask, op, o->pitch, N, C, scale);
-    else if (hd == 32) window_attn_kernel<32><<<grid, 64, 0, st>>>(qp, qkv->pitch, bias, mask, n_mask, op, o->pitch, N, C, scale);
-    else window_attn_kernel<16><<<grid, 64, 0, st>>>(qp, qkv->pitch, bias, mask, n_mask, op, o->pitch, N, C, scale);
+    if (hd == 64) window_attn_kernel<64><<<grid, 64, 0, st>>>(qp, qkv->pitch, bias, mask, n_mask, op, o->pitch, N, C, scale, 0, 0, 1, 1);
+    else if (hd == 32) window_attn_kernel<32><<<grid, 64, 0, st>>>(qp, qkv->pitch, bias, mask, n_mask, op, o->pitch, N, C, scale, 0, 0, 1, 1);
+    else window_attn_kernel<16><<<grid, 64, 0, st>>>(qp, qkv->pitch, bias, mask, n_mask, op, o->pitch, N, C, scale, 0, 0, 1, 1);
+    SKB_LAUNCH_CHECK();
+    return SKB_OK;
+}
+
+extern "C" int skb_window_attn2d_bf16(const skb_view* qkv, const float* bias, const float* mask, int32_t n_mask, const skb_view* o,
+                                      int32_t heads, int32_t window, float scale, void* stream) {
+    int rc = check_device();
+    if (rc != SKB_OK) return rc;
+    SKB_REQUIRE(qkv && o && bias && qkv->ptr && o->ptr && qkv->dtype == SKB_BF16 && o->dtype == SKB_BF16, SKB_ERR_ARG, "window_attn2d: bad views");
+    const int C = o->c;
+    SKB_REQUIRE(heads >= 1 && qkv->c == 3 * C && C % heads == 0, SKB_ERR_ARG, "window_attn2d: C=%d heads=%d qkv channels=%d", C, heads, qkv->c);
+    const int hd = C / heads;
+    SKB_REQUIRE(hd == 16 || hd == 32 || hd == 64, SKB_ERR_UNSUPPORTED, "window_attn2d: head_dim %d (supported: 16, 32, 64)", hd);
+    SKB_REQUIRE(window >= 1 && window <= 8, SKB_ERR_UNSUPPORTED, "window_attn2d: window %d (supported: 1..8, i.e. <= 64 tokens)", window);
+    SKB_REQUIRE(qkv->n == o->n && qkv->h == o->h && qkv->w == o->w && qkv->h % window == 0 && qkv->w % window == 0, SKB_ERR_ARG,
+                "window_attn2d: maps must agree and be multiples of the window (%dx%d, window %d)", qkv->h, qkv->w, window);
+    SKB_REQUIRE(qkv->pitch % 8 == 0 && o->pitch % 8 == 0 && ((uintptr_t)qkv->ptr & 15) == 0 && ((uintptr_t)o->ptr & 15) == 0, SKB_ERR_ARG,
+                "window_attn2d: alignment");
+    SKB_REQUIRE(!mask || n_mask >= 1, SKB_ERR_ARG, "window_attn2d: mask given with n_mask=%d", n_mask);
+    const int N = window * window, wins_x = qkv->w / window, wpi = wins_x * (qkv->h / window);
+    dim3 grid(qkv->n * wpi, heads);
+    cudaStream_t st = (cudaStream_t)stream;
+    const __nv_bfloat16* qp = (const __nv_bfloat16*)qkv->ptr;
+    __nv_bfloat16* op = (__nv_bfloat16*)o->ptr;
+    if (hd == 64) window_attn_kernel<64><<<grid, 64, 0, st>>>(qp, qkv->pitch, bias, mask, n_mask, op, o->pitch, N, C, scale, window, qkv->w, wins_x, wpi);
+    else if (hd == 32) window_attn_kernel<32><<<grid, 64, 0, st>>>(qp, qkv->pitch, bias, mask, n_mask, op, o->pitch, N, C, scale, window, qkv->w, wins_x, wpi);
+    else window_attn_kernel<16><<<grid, 64, 0, st>>>(qp, qkv->pitch, bias, mask, n_mask, op, o->pitch, N, C, scale, window, qkv->w, wins_x, wpi);
     SKB_LAUNCH_CHECK();
     return SKB_OK;
 }

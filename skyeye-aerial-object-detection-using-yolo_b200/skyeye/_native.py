@@ -103,6 +103,8 @@ _SIGNATURES = {
     "skb_flash_attn_bf16": (c_int32, [POINTER(skb_view), POINTER(skb_view), c_int32, c_float, c_void_p]),
     "skb_debug_attn_prof": (c_int32, [c_void_p, c_int32]),
     "skb_window_attn_bf16": (c_int32, [POINTER(skb_view), c_void_p, c_void_p, c_int32, POINTER(skb_view), c_int32, c_float, c_void_p]),
+    "skb_window_attn2d_bf16": (c_int32, [POINTER(skb_view), c_void_p, c_void_p, c_int32, POINTER(skb_view), c_int32, c_int32, c_float,
+                                         c_void_p]),
     "skb_decode_f32": (c_int32, [POINTER(skb_view), c_int32, c_int32, c_int32, POINTER(c_float), c_int32, c_int32,
                                  c_void_p, POINTER(c_void_p), c_void_p]),
     "skb_nms_workspace_bytes": (c_size_t, [c_int32]),

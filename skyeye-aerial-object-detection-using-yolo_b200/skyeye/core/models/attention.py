@@ -202,3 +202,72 @@ class WindowedSelfAttention(nn.Module):
         out = self.lower(plan, xin, mask)
         plan.run()
         return out.torch().squeeze(1).float()
+
+
+def window_partition(x: torch.Tensor, window: int) -> torch.Tensor:
+    """[B, H, W, C] -> [B * nW, window * window, C], windows row-major over the window grid (the input layout
+    WindowedSelfAttention.forward documents, reference attention.py:358-365; the reference ships no partition helper)."""
+    B, H, W, C = x.shape
+    x = x.view(B, H // window, window, W // window, window, C)
+    return x.permute(0, 1, 3, 2, 4, 5).reshape(-1, window * window, C)
+
+
+def window_reverse(windows: torch.Tensor, window: int, H: int, W: int) -> torch.Tensor:
+    """Inverse of ``window_partition``: [B * nW, window * window, C] -> [B, H, W, C]."""
+    B = windows.shape[0] // ((H // window) * (W // window))
+    x = windows.view(B, H // window, W // window, window, window, -1)
+    return x.permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, -1)
+
+
+class WindowedTransformerLayer(nn.Module):
+    """``head: windowed`` (NOT IN REFERENCE): TransformerLayer (attention.py:244-309) with its global
+    nn.MultiheadAttention replaced by the reference's WindowedSelfAttention class (attention.py:312-399) over non-overlapping
+    ``window_size`` x ``window_size`` windows -- O(N w^2) instead of O(N^2):
+        t = t + reverse(attn(partition(norm1(t))));  t = t + feedforward(norm2(t)).
+    Partition and reverse never run: qkv / proj are per-token GEMMs on the whole map and the attention kernel addresses
+    the windows in place (skb_window_attn2d_bf16)."""
+
+    def __init__(self, dim, num_heads, window_size=8, feedforward_dim=None, dropout=0.1):
+        super().__init__()
+        feedforward_dim = dim * 4 if feedforward_dim is None else feedforward_dim
+        self.attn = WindowedSelfAttention(dim, window_size, num_heads)
+        self.norm1 = nn.LayerNorm(dim)
+        self.norm2 = nn.LayerNorm(dim)
+        self.feedforward = nn.Sequential(nn.Linear(dim, feedforward_dim), nn.ReLU(inplace=True), nn.Dropout(dropout),
+                                         nn.Linear(feedforward_dim, dim), nn.Dropout(dropout))
+        self.dim, self.num_heads, self.window_size = dim, num_heads, window_size
+
+    def lower(self, plan: Plan, x: View, out: View = None, name="wtl") -> View:
+        dev, C, ws, a = plan.device, self.dim, self.window_size, self.attn
+        n, h, w = x.n, x.h, x.w
+        if h % ws or w % ws:
+            raise ValueError(f"windowed head: the {h}x{w} level map is not a multiple of window_size {ws}")
+        f32 = lambda t: t.detach().float().to(dev).contiguous()
+        g1, b1, g2, b2 = f32(self.norm1.weight), f32(self.norm1.bias), f32(self.norm2.weight), f32(self.norm2.bias)
+        n_tok = ws * ws
+        bias = a.relative_position_bias_table.detach().float()[a.relative_position_index.view(-1)]
+        bias = bias.view(n_tok, n_tok, self.num_heads).permute(2, 0, 1).contiguous().to(dev)
+        plan.keep += [g1, b1, g2, b2, bias]
+        xn = plan.buf(n, h, w, C)
+        plan.add(name + ".ln1", lambda s: L.E.layernorm(x, g1, b1, xn, self.norm1.eps, s), "layernorm", 0.0, 4.0 * n * h * w * C,
+                 outs=[dict(view=xn, label=L.ref(self, ".ln1"))])
+        qkv = plan.buf(n, h, w, 3 * C)
+        plan.conv(name + ".qkv", xn, PackedConv(a.qkv.weight, a.qkv.bias, dev), qkv, 1, ACT_NONE, label=L.ref(self, ".qkv"))
+        o = plan.buf(n, h, w, C)
+        plan.add(name + ".attn", lambda s: L.E.window_attn2d(qkv, bias, None, o, self.num_heads, ws, a.scale, s), "attention",
+                 4.0 * n * h * w * n_tok * C, 2.0 * n * h * w * 4 * C, outs=[dict(view=o, label=L.ref(self, ".attn"))])
+        t = plan.buf(n, h, w, C)
+        plan.conv(name + ".proj", o, PackedConv(a.proj.weight, a.proj.bias, dev), t, 1, ACT_NONE, x, label=L.ref(self, ".proj"))
+        xn2 = plan.buf(n, h, w, C)
+        plan.add(name + ".ln2", lambda s: L.E.layernorm(t, g2, b2, xn2, self.norm2.eps, s), "layernorm", 0.0, 4.0 * n * h * w * C,
+                 outs=[dict(view=xn2, label=L.ref(self, ".ln2"))])
+        ff0, ff3 = self.feedforward[0], self.feedforward[3]
+        hid = plan.buf(n, h, w, ff0.out_features)
+        plan.conv(name + ".ff0", xn2, PackedConv(ff0.weight, ff0.bias, dev), hid, 1, ACT_RELU, label=L.ref(self, ".ff0"))
+        if out is None:
+            out = plan.buf(n, h, w, C)
+        return plan.conv(name + ".ff3", hid, PackedConv(ff3.weight, ff3.bias, dev), out, 1, ACT_NONE, t, label=L.ref(self, ".ff3"))
+
+    def forward(self, x):
+        return L.run_module(self, x)
+

@@ -20,7 +20,7 @@ import yaml
 from ... import engine as E
 from .. import _lowering as L
 from ...engine import ACT_NONE, PackedConv, Plan, View
-from .attention import CrossLayerAttention, TransformerLayer
+from .attention import CrossLayerAttention, TransformerLayer, WindowedTransformerLayer
 from .backbone import SkyEyeBackbone
 from .blocks import ConvolutionBlock, CSPBlock
 
@@ -386,11 +386,17 @@ class EnhancedSkyEyeDetector(SkyEyeDetector):
         self.cross_attention_p4_p3 = CrossLayerAttention(c3, c4, region_size=2, heads=4)
         # default = the reference architecture (bare 1x1 heads, detector.py:436-501); the transformer heads of the skyeye_l
         # variant are selected by "head: transformer" in the model config
-        if self.cfg.get("head", "conv") == "transformer":
-            hd = self.cfg.get("head_dim", 64)
+        # "head: windowed"  swaps the global attention for the reference's WindowedSelfAttention class
+        head, hd = self.cfg.get("head", "conv"), self.cfg.get("head_dim", 64)
+        if head == "transformer":
             self.head_transformers = nn.ModuleList(TransformerLayer(c, max(c // hd, 1)) for c in (c3, c4, c5))
-        else:
+        elif head == "windowed":
+            ws = self.cfg.get("window_size", 8)
+            self.head_transformers = nn.ModuleList(WindowedTransformerLayer(c, max(c // hd, 1), ws) for c in (c3, c4, c5))
+        elif head == "conv":
             self.head_transformers = None
+        else:
+            raise ValueError(f"head: {head!r} (expected conv | transformer | windowed)")
         self._initialize_weights()
         self.eval()
         if weights is not None:
@@ -413,7 +419,7 @@ def parse_model(model_cfg, in_channels=3) -> dict:
     return {"base_channels": cfg.get("base_channels", 64), "depth_multiple": cfg.get("depth_multiple", 1.0),
             "width_multiple": cfg.get("width_multiple", 1.0), "nc": cfg.get("nc", 80), "in_channels": in_channels,
             "anchors": cfg.get("anchors"), "detector": cfg.get("detector", "base"), "head": cfg.get("head", "conv"),
-            "head_dim": cfg.get("head_dim", 64)}
+            "head_dim": cfg.get("head_dim", 64), "window_size": cfg.get("window_size", 8)}
 
 
 def construct_model(model_cfg, in_channels=3, num_classes=None, anchors=None):

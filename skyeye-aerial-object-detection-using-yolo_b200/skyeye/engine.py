@@ -207,6 +207,14 @@ def window_attn(qkv: View, bias: torch.Tensor, mask: Optional[torch.Tensor], o: 
                                          _stream_ptr() if stream is None else stream), "skb_window_attn_bf16")
 
 
+def window_attn2d(qkv: View, bias: torch.Tensor, mask: Optional[torch.Tensor], o: View, heads: int, window: int, scale: float,
+                  stream=None) -> None:
+    """Window attention on unpartitioned feature maps [B,H,W,.]: partition / reverse are the kernel's addressing."""
+    N.check(N.lib().skb_window_attn2d_bf16(qkv.ref, bias.data_ptr(), mask.data_ptr() if mask is not None else None,
+                                           mask.shape[0] if mask is not None else 0, o.ref, heads, window, scale,
+                                           _stream_ptr() if stream is None else stream), "skb_window_attn2d_bf16")
+
+
 def decode(raws: Sequence[View], na: int, no: int, anchors, in_hw, det: torch.Tensor,
            raw_out: Optional[Sequence[torch.Tensor]] = None, stream=None) -> None:
     L = len(raws)
