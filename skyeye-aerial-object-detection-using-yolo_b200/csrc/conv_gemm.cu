@@ -503,13 +503,21 @@ struct HaloParams {
     const float* bias;
     int act, has_res;
     long long* trace;
+    // tap list: tap t reads the halo box at (dy, dx) = (t / tdiv, t % tdiv); the box's origin is (w0 + w_org, h0 + h_org).
+    // 3x3: ntaps 9, tdiv 3, origin (-1, -1).  Focus (row taps over pre-shifted 4-pixel windows): ntaps 3, tdiv 1, origin (0, -1).
+    int ntaps, tdiv, w_org, h_org;
 };
 
-template <int BN>
+// HW = pixels per halo-box row: 24 for the 3x3 convs (16 + 2 halo pixels, padded to 3 swizzle atoms), 16 for the Focus row-tap
+// conv (its column taps live inside the 4-pixel windows).  The smaller Focus box leaves room for THREE halo stages: a Focus tile
+// has only 3 taps x 4 MMAs of work per box (768 tensor cycles), so with two stages the ~1.5 us HBM latency of the single box in
+// flight paced the kernel (3600 cycles per tile measured).
+template <int BN, int HW = 24>
 struct HaloCfg {
-    static constexpr int HALO_W = 24, HALO_H = 18;
-    static constexpr int HALO_BYTES = HALO_H * HALO_W * 128;  // 55296
-    static constexpr int HS = 2;                              // halo stages
+    static constexpr int HALO_W = HW, HALO_H = 18;
+    static constexpr int HALO_BYTES = HALO_H * HALO_W * 128;  // 55296 / 36864
+    static constexpr int ROW_BYTES = HALO_W * 128;            // one halo-box row = the stride between 8-pixel row groups
+    static constexpr int HS = HW == 24 ? 2 : 3;               // halo stages (HW 16, BN 64: 3 x 36 KB + 6 weight stages)
     static constexpr int B_BYTES = BN * 128;
     static constexpr int EPI_NB = BN == 64 ? 2 : 1;           // staging slots per epilogue group
     static constexpr int EPI_BUF = 16384;
@@ -528,11 +536,11 @@ __device__ __forceinline__ void halo_decode(const HaloParams& p, int item, int& 
     w0 = iw * 16; h0 = ih * 16;
 }
 
-template <int BN>
+template <int BN, int HW>
 __global__ void __launch_bounds__(384, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const HaloParams p) {
-    using Cfg = HaloCfg<BN>;
+    using Cfg = HaloCfg<BN, HW>;
     constexpr int HS = Cfg::HS, BS = Cfg::BS, NB = Cfg::EPI_NB;
 
     extern __shared__ uint8_t smem_raw[];
@@ -592,7 +600,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     mbar_wait(h_empty(hs), hph ^ 1);
                     if (lead) {
                         mbar_expect_tx(h_full(hs), (uint32_t)Cfg::HALO_BYTES);
-                        tma_load_4d(sH0 + hs * Cfg::HALO_BYTES, &tmA, h_full(hs), c * 64, w0 - 1, h0 - 1, n);  // borders: zero fill
+                        tma_load_4d(sH0 + hs * Cfg::HALO_BYTES, &tmA, h_full(hs), c * 64, w0 + p.w_org, h0 + p.h_org, n);  // borders: zero fill
                     }
                     if (++hs == HS) { hs = 0; hph ^= 1; }
                 }
@@ -607,7 +615,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 int nb, w0, h0, n;
                 halo_decode(p, item, nb, w0, h0, n);
                 for (int c = 0; c < p.cchunks; ++c)
-                    for (int t = 0; t < 9; ++t) {
+                    for (int t = 0; t < p.ntaps; ++t) {
                         mbar_wait(b_empty(bs), bph ^ 1);
                         if (lead) {
                             mbar_expect_tx(b_full(bs), (uint32_t)Cfg::B_BYTES);
@@ -633,21 +641,21 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int c = 0; c < p.cchunks; ++c) {
                 mbar_wait(h_full(hs), hph);
                 const uint32_t hbase = sH0 + hs * Cfg::HALO_BYTES;
-                for (int t = 0; t < 9; ++t) {
+                for (int t = 0; t < p.ntaps; ++t) {
                     mbar_wait(b_full(bs), bph);
                     tc_fence_after();
                     if (lead) {
-                        const int dy = t / 3, dx = t - dy * 3;
-                        const uint32_t a0 = hbase + (uint32_t)(dy * 3072 + dx * 128 + half * 1024);  // right half: 8 pixels further
+                        const int dy = t / p.tdiv, dx = t - dy * p.tdiv;
+                        const uint32_t a0 = hbase + (uint32_t)(dy * Cfg::ROW_BYTES + dx * 128 + half * 1024);  // right half: 8 pixels further
                         // start not 1024-aligned when dx != 0: the 128B-swizzle XOR is taken from the absolute smem
                         // address bits [7,10) (measured: correct with the descriptor's base-offset field left 0)
-                        const uint64_t ad0 = umma_desc(a0, 16, 3072, UMMA_SW128);
+                        const uint64_t ad0 = umma_desc(a0, 16, Cfg::ROW_BYTES, UMMA_SW128);
                         const uint64_t bd = umma_desc(sB0 + bs * Cfg::B_BYTES, 16, 1024, UMMA_SW128);
                         const uint32_t acc = (c > 0 || t > 0) ? 1u : 0u;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) umma_bf16_ss(d0, ad0 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (acc || k > 0) ? 1u : 0u);
                         umma_commit(b_empty(bs));
-                        if (t == 8) {
+                        if (t == p.ntaps - 1) {
                             umma_commit(h_empty(hs));
                             if (c == p.cchunks - 1) umma_commit(tfull(buf, half));
                         }
@@ -760,13 +768,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN>
+template <int BN, int HW = 24>
 static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR, const HaloParams& p,
                        cudaStream_t stream) {
-    using Cfg = HaloCfg<BN>;
+    using Cfg = HaloCfg<BN, HW>;
     static PerDeviceOnce attr_once;
     if (attr_once.first())
-        SKB_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        SKB_CUDA((cudaFuncSetAttribute(conv3x3_halo_kernel<BN, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)));
     const int grid = p.total_items < num_sms() ? p.total_items : num_sms();
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -779,7 +787,7 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    SKB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<BN>, tmA, tmB, tmY, tmR, p));
+    SKB_CUDA((cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<BN, HW>, tmA, tmB, tmY, tmR, p)));
     return SKB_OK;
 }
 
@@ -900,6 +908,7 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
             hp.fd_nb = make_fastdiv(hp.n_blocks); hp.fd_tw = make_fastdiv(tw16); hp.fd_th = make_fastdiv(th16);
             hp.cchunks = Cin / 64; hp.cin = Cin; hp.cout = y->c;
             hp.bias = bias; hp.act = act; hp.has_res = residual ? 1 : 0; hp.trace = g_conv_trace;
+            hp.ntaps = 9; hp.tdiv = 3; hp.w_org = -1; hp.h_org = -1;
             CUtensorMap tmA, tmB, tmY, tmR;
             const uint64_t pitchB = (uint64_t)x->pitch * 2;
             uint64_t ad[4] = {(uint64_t)Cin, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
@@ -955,7 +964,14 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
             const char* e = getenv("SKB_CONV_PAIR");
             pair_mode = e ? atoi(e) : 1;
         }
-        const bool pair_ok = pair_mode != 0 && !upsample2x && taps * Cin >= 256 && m_tiles >= 2;
+        // K = 256 layers (qkv, ff0, the 256-channel 1x1s) run 5-12 % faster unpaired when timed alone (scripts/tune_conv.py,
+        // profiles/r2d_tune_conv.txt): too few k-iterations per tile to amortise the pair's cross-CTA hand-offs
+        static int pair_min_k = -1;
+        if (pair_min_k < 0) {
+            const char* e = getenv("SKB_CONV_PAIR_MIN_K");
+            pair_min_k = e ? atoi(e) : 512;
+        }
+        const bool pair_ok = pair_mode != 0 && !upsample2x && taps * Cin >= pair_min_k && m_tiles >= 2;
         double best = 1e30;
         const int cands[4] = {256, 128, 64, 32};
         const double pen1[4] = {1.5, 2.0, 3.0, 5.0};
@@ -972,6 +988,15 @@ extern "C" int skb_conv2d_bf16(const skb_view* x, const void* w_packed, const fl
                     NCTA = nc;
                 }
             }
+    }
+    {   // tuning override (not part of the ABI): SKB_CONV_FORCE="BN,NCTA" is re-read on every call (scripts/tune_conv.py)
+        const char* e = getenv("SKB_CONV_FORCE");
+        int fbn = 0, fnc = 0;
+        if (e && sscanf(e, "%d,%d", &fbn, &fnc) == 2 && (fbn == 32 || fbn == 64 || fbn == 128 || fbn == 256) && (fnc == 1 || fnc == 2) &&
+            cout_pad % fbn == 0 && !(fnc == 2 && (fbn < 64 || upsample2x || m_tiles < 2))) {
+            BN = fbn;
+            NCTA = fnc;
+        }
     }
     p.n_blocks = cout_pad / BN;
     p.total_tiles = cdiv(m_tiles, NCTA) * p.n_blocks;  // work items: one per CTA, or per CTA pair
@@ -1116,6 +1141,49 @@ static int focus_conv_impl(const void* img, int32_t img_dtype, int32_t n, int32_
     cudaStream_t st = (cudaStream_t)stream;
     rc = launch_focus_pad(img, img_dtype, n, h, w, scratch, st, tiles, frame_h, frame_w);
     if (rc != SKB_OK) return rc;
+
+    // Halo form (default): a 16 x 16 output tile takes ONE TMA box of 18 rows x 16 windows from the padded scratch and its three
+    // row taps read that box in place (conv3x3_halo_kernel with the tap list (0,0) (1,0) (2,0)): 36 KB of activations + 24 KB of
+    // weights per 256 pixels instead of 144 KB with one box per row tap -- the per-tap form was bound by bytes entering the SM.
+    {
+        static int focus_halo = -1;  // tuning knob (not part of the ABI): SKB_FOCUS_HALO=0 keeps the per-tap generic kernel
+        if (focus_halo < 0) {
+            const char* e = getenv("SKB_FOCUS_HALO");
+            focus_halo = e ? atoi(e) : 1;
+        }
+        const int th16 = cdiv(Ho, 16), tw16 = cdiv(Wo, 16);
+        const double cover = (double)th16 * 16 * tw16 * 16 / ((double)Ho * Wo);
+        if (focus_halo && cout_pad % 64 == 0 && cover <= 1.2) {
+            const int BN = cout_pad % 128 == 0 ? 128 : 64;
+            HaloParams hp;
+            memset(&hp, 0, sizeof(hp));
+            hp.tiles_w = tw16; hp.tiles_h = th16;
+            hp.n_blocks = cout_pad / BN;
+            hp.total_items = tw16 * th16 * n * hp.n_blocks;
+            hp.fd_nb = make_fastdiv(hp.n_blocks); hp.fd_tw = make_fastdiv(tw16); hp.fd_th = make_fastdiv(th16);
+            hp.cchunks = 1; hp.cin = 64; hp.cout = y->c;
+            hp.bias = bias; hp.act = act; hp.has_res = 0; hp.trace = g_conv_trace;
+            hp.ntaps = 3; hp.tdiv = 1; hp.w_org = 0; hp.h_org = -1;
+            CUtensorMap tmA, tmB, tmY;
+            // window (n, oy, ox) = 64 elements starting at scratch pixel ox of padded row oy (32 B per pixel: overlapping rows)
+            uint64_t ad[4] = {64, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)n};
+            uint64_t as[3] = {32, (uint64_t)Wp * 32, (uint64_t)Wp * 32 * Ho};
+            uint32_t ab[4] = {64u, 16u, 18u, 1u};
+            rc = encode_tensor_map(&tmA, scratch, 2, 4, ad, as, ab, 128);
+            if (rc != SKB_OK) return rc;
+            uint64_t bd[2] = {192, (uint64_t)cout_pad};
+            uint64_t bs[1] = {192 * 2};
+            uint32_t bb[2] = {64u, (uint32_t)BN};
+            rc = encode_tensor_map(&tmB, w_rowtap, 2, 2, bd, bs, bb, 128);
+            if (rc != SKB_OK) return rc;
+            uint64_t yd[4] = {(uint64_t)y->c, (uint64_t)y->w, (uint64_t)y->h, (uint64_t)y->n};
+            uint64_t ys[3] = {(uint64_t)y->pitch * 2, (uint64_t)y->pitch * 2 * y->w, (uint64_t)y->pitch * 2 * y->w * y->h};
+            uint32_t yb[4] = {64u, 8u, 16u, 1u};
+            rc = encode_tensor_map(&tmY, y->ptr, 2, 4, yd, ys, yb, 128);
+            if (rc != SKB_OK) return rc;
+            return BN == 128 ? launch_halo<128, 16>(tmA, tmB, tmY, tmB, hp, st) : launch_halo<64, 16>(tmA, tmB, tmY, tmB, hp, st);
+        }
+    }
 
     ConvParams p;
     memset(&p, 0, sizeof(p));
