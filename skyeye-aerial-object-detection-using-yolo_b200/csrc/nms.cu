@@ -11,7 +11,11 @@
 //     most max_det of them (metrics.py:443-444), so each image needs <= n*max_det IoU tests instead of
 //     n^2/2: one CTA per image walks the sorted candidates in chunks with the kept list in shared
 //     memory (warp-ballot compaction, no n x n mask in HBM).
-#include <cub/cub.cuh>
+// Ordering is done in the kernels themselves (no library sort): the filter compacts the surviving keys per image, and the
+// image's CTA orders them LAZILY in shared memory -- an exact radix SELECT of the next (up to) 8192 best keys, a bitonic sort
+// of those, the greedy pass over them, and only if max_det boxes have not been kept yet the next 8192.  A detector's image
+// needs one round; the worst case (30 000 candidates, nothing suppressed... all walked) needs four.
+#include <float.h>
 
 #include "common.cuh"
 
@@ -29,14 +33,272 @@ __device__ __forceinline__ bool iou_gt(float ax1, float ay1, float ax2, float ay
     return ovr > thr;  // NaN (0/0) never suppresses
 }
 
+__device__ __forceinline__ unsigned int desc_bits(float s) {
+    unsigned int u = __float_as_uint(s);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending-orderable
+    return ~u;                                       // descending
+}
+
+// =============================================================================================
+// (0) CTA-wide ordering of unique 64-bit keys that live in global memory (512 threads)
+// =============================================================================================
+constexpr int NMS_THREADS = 512;
+constexpr int SORT_KS = 8192;               // keys ordered per round in shared memory (64 KB)
+constexpr int SEL_BITS = 11, SEL_BINS = 1 << SEL_BITS;
+constexpr int SEL_SMALL = SEL_BINS / 2;     // a digit bin this small is resolved by rank counting (its keys alias the histogram)
+static_assert(SEL_BINS == 4 * NMS_THREADS, "one thread owns four histogram bins");
+
+struct alignas(16) SortScratch {
+    unsigned int hist[SEL_BINS];  // aliased as unsigned long long small[SEL_SMALL]
+    unsigned int warp_tot[NMS_THREADS / 32];
+    int sel_bin, sel_cnt, n_small, n_out;
+    unsigned int sel_below;
+    unsigned long long result;
+};
+
+// f(key) for every key of g[0, n): eight independent coalesced loads per thread are in flight before the first is used (the
+// one-load-per-iteration form was latency-bound: ~700 cycles per key and thread, 0.4 ms for a 100 000-key image).
+template <typename F>
+__device__ __forceinline__ void cta_for_each_key(const unsigned long long* g, int n, F f) {
+    constexpr int U = 8;
+    for (int base = 0; base < n; base += NMS_THREADS * U) {
+        unsigned long long kbuf[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * NMS_THREADS + (int)threadIdx.x;
+            kbuf[u] = i < n ? g[i] : 0ULL;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (base + u * NMS_THREADS + (int)threadIdx.x < n) f(kbuf[u]);
+    }
+}
+
+// The k-th smallest (k >= 1) of the keys in g[0, n) that are > lo (all keys if !have_lo).  Only the low `total_bits` bits
+// differ between the keys of a segment, and their top `common_bits` bits are known to be equal as well (value `common`,
+// right-aligned: sign and exponent of scores in (0, 1) -- without this the first digit would hit a handful of bins).  MSD
+// radix select: one 11-bit digit per pass over the keys (a histogram in shared memory), until the digit bin that holds the
+// answer has <= SEL_SMALL keys; those are ranked directly.  Keys are unique.
+__device__ unsigned long long cta_select_kth(const unsigned long long* g, int n, bool have_lo, unsigned long long lo, int k,
+                                             int total_bits, int common_bits, unsigned long long common, SortScratch& S) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long kmask = total_bits >= 64 ? ~0ULL : (1ULL << total_bits) - 1ULL;
+    auto shr = [](unsigned long long v, int sh) { return sh >= 64 ? 0ULL : v >> sh; };
+    unsigned long long prefix = common;  // resolved high bits of (key & kmask), right-aligned
+    int resolved = common_bits;
+    while (true) {
+        const int nb = min(SEL_BITS, total_bits - resolved);
+        const int shift = total_bits - resolved - nb;
+        for (int i = tid; i < SEL_BINS; i += NMS_THREADS) S.hist[i] = 0u;
+        __syncthreads();
+        cta_for_each_key(g, n, [&](unsigned long long key) {
+            const unsigned long long kk = key & kmask;
+            if ((!have_lo || key > lo) && shr(kk, shift + nb) == prefix) atomicAdd(&S.hist[(unsigned int)(kk >> shift) & ((1u << nb) - 1u)], 1u);
+        });
+        __syncthreads();
+        {   // the bin that holds the k-th key: thread t owns bins 4t .. 4t+3
+            unsigned int c[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c[q] = S.hist[4 * tid + q];
+            const unsigned int mine = c[0] + c[1] + c[2] + c[3];
+            unsigned int inc = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (lane == 31) S.warp_tot[warp] = inc;
+            __syncthreads();
+            unsigned int base = 0;
+            for (int w = 0; w < warp; ++w) base += S.warp_tot[w];
+            unsigned int excl = base + inc - mine;
+            if (excl < (unsigned int)k && (unsigned int)k <= excl + mine) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if ((unsigned int)k <= excl + c[q]) { S.sel_bin = 4 * tid + q; S.sel_below = excl; S.sel_cnt = (int)c[q]; break; }
+                    excl += c[q];
+                }
+            }
+            __syncthreads();
+        }
+        const int cnt = S.sel_cnt;
+        k -= (int)S.sel_below;
+        prefix = (prefix << nb) | (unsigned long long)S.sel_bin;
+        resolved += nb;
+        if (resolved == total_bits) return (g[0] & ~kmask) | prefix;  // every bit resolved (the bin holds exactly the key)
+        if (cnt <= SEL_SMALL) {
+            unsigned long long* small = reinterpret_cast<unsigned long long*>(S.hist);
+            __syncthreads();  // everyone has read sel_* and the histogram
+            if (tid == 0) S.n_small = 0;
+            __syncthreads();
+            const int sh = total_bits - resolved;
+            cta_for_each_key(g, n, [&](unsigned long long key) {
+                if ((!have_lo || key > lo) && shr(key & kmask, sh) == prefix) small[atomicAdd(&S.n_small, 1)] = key;
+            });
+            __syncthreads();
+            for (int t = tid; t < cnt; t += NMS_THREADS) {
+                const unsigned long long mk = small[t];
+                int r = 0;
+                for (int j = 0; j < cnt; ++j) r += small[j] < mk ? 1 : 0;
+                if (r == k - 1) S.result = mk;
+            }
+            __syncthreads();
+            return S.result;
+        }
+        __syncthreads();  // the histogram is rebuilt by the next pass
+    }
+}
+
+// dst[0, m) <- the keys of g[0, n) in (lo, hi] (order unspecified); returns m to every thread.  At most `cap` keys are stored:
+// m > cap tells the caller that the range was too wide.
+__device__ int cta_gather_range(const unsigned long long* g, int n, bool have_lo, unsigned long long lo, unsigned long long hi,
+                                unsigned long long* dst, int cap, SortScratch& S) {
+    if (threadIdx.x == 0) S.n_out = 0;
+    __syncthreads();
+    cta_for_each_key(g, n, [&](unsigned long long key) {
+        if ((!have_lo || key > lo) && key <= hi) {
+            const int pos = atomicAdd(&S.n_out, 1);
+            if (pos < cap) dst[pos] = key;
+        }
+    });
+    __syncthreads();
+    return S.n_out;
+}
+
+// A cut `hi` such that (lo, hi] probably holds between 1 and SORT_KS keys, from a histogram of the first undetermined digit
+// over a strided SAMPLE of the segment (shared-memory atomics cost ~2 cycles per key: a full histogram of a 100 000-key
+// image was 0.12 ms).  The caller counts the range exactly while gathering it and falls back to cta_select_kth if the
+// estimate was off (adversarial score distributions: everything inside one digit bin).
+__device__ unsigned long long cta_sampled_cut(const unsigned long long* g, int n, bool have_lo, unsigned long long lo, int want,
+                                              int total_bits, int common_bits, unsigned long long common, SortScratch& S) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long kmask = total_bits >= 64 ? ~0ULL : (1ULL << total_bits) - 1ULL;
+    const int nb = min(SEL_BITS, total_bits - common_bits);
+    const int shift = total_bits - common_bits - nb;
+    const int stride = max(1, n >> 12);  // <= 8192 samples
+    for (int i = tid; i < SEL_BINS; i += NMS_THREADS) S.hist[i] = 0u;
+    __syncthreads();
+    for (int j = tid; (long)j * stride < n; j += NMS_THREADS) {
+        const unsigned long long key = g[(long)j * stride];
+        if (!have_lo || key > lo) atomicAdd(&S.hist[(unsigned int)((key & kmask) >> shift) & ((1u << nb) - 1u)], 1u);
+    }
+    __syncthreads();
+    const unsigned int target = (unsigned int)max(1, (want - want / 4) / stride);  // aim at 3/4 of the capacity
+    unsigned int c[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c[q] = S.hist[4 * tid + q];
+    const unsigned int mine = c[0] + c[1] + c[2] + c[3];
+    unsigned int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) S.warp_tot[warp] = inc;
+    if (tid == 0) S.sel_bin = SEL_BINS - 1;  // fewer samples than the target: take everything that is left
+    __syncthreads();
+    unsigned int base = 0;
+    for (int w = 0; w < warp; ++w) base += S.warp_tot[w];
+    unsigned int excl = base + inc - mine;
+    if (excl < target && target <= excl + mine) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (target <= excl + c[q]) { S.sel_bin = 4 * tid + q; break; }
+            excl += c[q];
+        }
+    }
+    __syncthreads();
+    const unsigned long long bin = (unsigned long long)S.sel_bin;
+    __syncthreads();
+    if (bin >= (1ULL << nb) - 1ULL) return ~0ULL;
+    const unsigned long long low_ones = shift ? ((1ULL << shift) - 1ULL) : 0ULL;
+    return (g[0] & ~kmask) | (((common << nb) | bin) << shift) | low_ones;  // upper edge of the digit bin
+}
+
+// ascending bitonic sort of a[0, m) in shared memory (padded to a power of two with all-ones keys, which sort last)
+__device__ void cta_bitonic_sort(unsigned long long* a, int m) {
+    int P = 2;
+    while (P < m) P <<= 1;
+    for (int i = m + threadIdx.x; i < P; i += NMS_THREADS) a[i] = ~0ULL;
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int idx = threadIdx.x; idx < (P >> 1); idx += NMS_THREADS) {
+                const int i = ((idx & ~(j - 1)) << 1) | (idx & (j - 1));
+                const int l = i | j;
+                const unsigned long long x = a[i], y = a[l];
+                if ((x > y) == ((i & k) == 0)) { a[i] = y; a[l] = x; }
+            }
+            __syncthreads();
+        }
+}
+
+// The next batch of a segment in ascending key order: the smallest m keys greater than `lo` (1 <= m <= SORT_KS, about `want` of
+// them when more than `want` are left) are gathered into skeys and sorted.  Returns m (0 when nothing is left).
+// `remaining` = keys of the segment that are > lo; want <= SORT_KS.
+__device__ int cta_next_sorted_batch(const unsigned long long* g, int n, bool have_lo, unsigned long long lo, int remaining,
+                                     int want, int total_bits, int common_bits, unsigned long long common, unsigned long long* skeys,
+                                     SortScratch& S) {
+    if (remaining <= 0 || want <= 0) return 0;
+    int m;
+    if (remaining <= want) {
+        m = cta_gather_range(g, n, have_lo, lo, ~0ULL, skeys, SORT_KS, S);
+    } else {
+        // any non-empty prefix of the order that fits the buffer will do: cut at a sampled digit boundary, count exactly
+        // while gathering, and only if that misses (empty or too many) pay for the exact selection of `want` keys
+        const unsigned long long cut = cta_sampled_cut(g, n, have_lo, lo, want, total_bits, common_bits, common, S);
+        m = cta_gather_range(g, n, have_lo, lo, cut, skeys, SORT_KS, S);
+        if (m == 0 || m > SORT_KS) {
+            const unsigned long long hi = cta_select_kth(g, n, have_lo, lo, want, total_bits, common_bits, common, S);
+            m = cta_gather_range(g, n, have_lo, lo, hi, skeys, SORT_KS, S);
+        }
+    }
+    cta_bitonic_sort(skeys, m);
+    return m;
+}
+
 // =============================================================================================
 // (1) generic bit-exact NMS
 // =============================================================================================
-__global__ void iota_kernel(int* idx, int n) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) idx[i] = i;
-}
-__global__ void gather_boxes_kernel(const float4* __restrict__ boxes, const int* __restrict__ order, int n, float4* __restrict__ out) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = boxes[order[i]];
+// One CTA orders the boxes by (score descending, index ascending) = torchvision's stable descending sort: keys
+// [~score | index] are written to scratch, then consumed batch by batch in ascending order; the batch's original indices and
+// boxes go straight to `order` / `sboxes` (no separate iota / sort / gather launches).
+__global__ void __launch_bounds__(NMS_THREADS)
+nms_order_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, int n, unsigned long long* __restrict__ keys,
+                 int* __restrict__ order, float4* __restrict__ sboxes) {
+    extern __shared__ __align__(16) uint8_t sort_smem[];
+    unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sort_smem);
+    SortScratch& S = *reinterpret_cast<SortScratch*>(sort_smem + (size_t)SORT_KS * 8);
+    unsigned int v_or = 0u, v_and = ~0u;
+    for (int i = threadIdx.x; i < n; i += NMS_THREADS) {
+        const unsigned int d = desc_bits(scores[i]);
+        v_or |= d;
+        v_and &= d;
+        keys[i] = ((unsigned long long)d << 32) | (unsigned int)i;
+    }
+    v_or = __reduce_or_sync(0xffffffffu, v_or);
+    v_and = __reduce_and_sync(0xffffffffu, v_and);
+    if ((threadIdx.x & 31) == 0) { S.hist[threadIdx.x >> 5] = v_or; S.hist[32 + (threadIdx.x >> 5)] = v_and; }
+    __syncthreads();
+    for (int w = 0; w < NMS_THREADS / 32; ++w) { v_or |= S.hist[w]; v_and &= S.hist[32 + w]; }
+    __syncthreads();
+    const int common_bits = __clz((int)(v_or ^ v_and));  // leading score bits every key shares (32 if all scores are equal)
+    const unsigned long long common = common_bits ? (unsigned long long)(v_or >> (32 - common_bits)) : 0ULL;
+    int consumed = 0;
+    bool have_lo = false;
+    unsigned long long lo = 0;
+    while (consumed < n) {
+        const int m = cta_next_sorted_batch(keys, n, have_lo, lo, n - consumed, SORT_KS, 64, common_bits, common, skeys, S);
+        for (int i = threadIdx.x; i < m; i += NMS_THREADS) {
+            const int idx = (int)(skeys[i] & 0xffffffffULL);
+            order[consumed + i] = idx;
+            sboxes[consumed + i] = boxes[idx];
+        }
+        lo = skeys[m - 1];
+        have_lo = true;
+        consumed += m;
+        __syncthreads();
+    }
 }
 // mask[i][cb] bit j: iou(sorted i, sorted cb*64 + j) > thr, only for column blocks >= row block
 __global__ void nms_mask_kernel(const float4* __restrict__ sb, int n, float thr, int col_blocks, unsigned long long* __restrict__ mask) {
@@ -81,29 +343,22 @@ __global__ void nms_reduce_kernel(const unsigned long long* __restrict__ mask, c
 }
 
 struct NmsWs {
-    float* keys_out;
-    int* idx_in;
+    unsigned long long* keys;
     int* idx_out;
     float4* sboxes;
     unsigned long long* mask;
-    void* cub_tmp;
-    size_t cub_bytes;
 };
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static size_t nms_layout(int n, void* base, NmsWs* ws) {
-    size_t cub_bytes = 0;
-    cub::DeviceRadixSort::SortPairsDescending(nullptr, cub_bytes, (const float*)nullptr, (float*)nullptr, (const int*)nullptr, (int*)nullptr, n);
     const int cbk = (n + 63) / 64;
     size_t off = 0;
     uint8_t* b = (uint8_t*)base;
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return b ? (void*)(b + o) : nullptr; };
-    void* k = take(sizeof(float) * n);
-    void* i0 = take(sizeof(int) * n);
+    void* k = take(sizeof(unsigned long long) * n);
     void* i1 = take(sizeof(int) * n);
     void* sb = take(sizeof(float4) * n);
     void* m = take(sizeof(unsigned long long) * (size_t)n * cbk);
-    void* c = take(cub_bytes);
-    if (ws) { ws->keys_out = (float*)k; ws->idx_in = (int*)i0; ws->idx_out = (int*)i1; ws->sboxes = (float4*)sb; ws->mask = (unsigned long long*)m; ws->cub_tmp = c; ws->cub_bytes = cub_bytes; }
+    if (ws) { ws->keys = (unsigned long long*)k; ws->idx_out = (int*)i1; ws->sboxes = (float4*)sb; ws->mask = (unsigned long long*)m; }
     return off + 256;
 }
 
@@ -114,7 +369,6 @@ static size_t nms_layout(int n, void* base, NmsWs* ws) {
 // the image field takes what is left of the upper 32 bits
 constexpr int KEY_MAX_SLOT_BITS = 27;
 constexpr int MAX_NMS_BOXES = 30000;  // metrics.py:393
-constexpr int NMS_THREADS = 512;
 constexpr int NMS_MAX_KEEP = 1024;
 
 struct FilterParams {
@@ -127,11 +381,6 @@ struct FilterParams {
     float classes[32];
 };
 
-__device__ __forceinline__ unsigned int desc_bits(float s) {
-    unsigned int u = __float_as_uint(s);
-    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending-orderable
-    return ~u;                                       // descending
-}
 __device__ __forceinline__ bool class_pass(const FilterParams& p, float col5) {
     if (p.n_classes <= 0) return true;
     for (int i = 0; i < p.n_classes; ++i)
@@ -139,69 +388,107 @@ __device__ __forceinline__ bool class_pass(const FilterParams& p, float col5) {
     return false;
 }
 
-// One thread per (image, box).  Every thread writes its own key slot(s): the sort key of a surviving
-// row or the all-ones sentinel (sorts last), so no position atomics are needed; the per-image counts
-// are warp-aggregated (one atomic per warp when the warp sits inside one image).
-__global__ void nms_filter_kernel(const FilterParams p, unsigned long long* __restrict__ keys, int* __restrict__ count) {
+// One thread per (image, box).  Surviving rows are appended to their image's key segment keys[b * stride ..) (stride = the
+// segment capacity N * keys-per-box) with warp-aggregated position atomics: the order inside a segment is arbitrary, the
+// consumer orders the (unique) keys.  key = [~score (32 bits) | slot]: ascending key = (score descending, row ascending) = the
+// reference's boolean-mask order + torchvision's stable sort.
+__global__ void nms_filter_kernel(const FilterParams p, unsigned long long* __restrict__ keys, int* __restrict__ count, long stride,
+                                  unsigned int* __restrict__ bits_or, unsigned int* __restrict__ bits_nor) {
     const long nbox = (long)p.B * p.N;
     const long nround = (nbox + blockDim.x - 1) / blockDim.x * blockDim.x;  // whole warps stay in the loop together
-    const int per = p.multi_label ? p.nc : 1;
     const int lane = threadIdx.x & 31;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nround; i += (long)gridDim.x * blockDim.x) {
         const bool inb = i < nbox;
         const int b = inb ? (int)(i / p.N) : -1;
-        int emitted = 0;
-        if (inb) {
-            const int r = (int)(i % p.N);
-            const float* x = p.pred + i * p.no;
-            const float obj = x[4];
-            unsigned long long* kout = keys + i * per;
-            const bool pass = obj > p.conf;  // metrics.py:391,402
-            auto key_of = [&](float score, int slot) {
-                return ((unsigned long long)b << (32 + p.slot_bits)) | ((unsigned long long)desc_bits(score) << p.slot_bits) |
-                       (unsigned long long)slot;
-            };
-            const unsigned long long none = ~0ULL;
-            if (p.nc > 1 || (p.compat == 1 && p.nc == 1)) {
-                if (p.multi_label) {  // metrics.py:407-410: one row per (box, class) above the threshold
-                    for (int j = 0; j < p.nc; ++j) {
-                        unsigned long long k = none;
-                        if (pass) {
-                            const float cp = x[5 + j];
-                            const float conf = p.compat ? __fmul_rn(cp, obj) : cp;
-                            if (conf > p.conf && class_pass(p, p.compat ? (float)j : cp)) { k = key_of(p.compat ? conf : obj, r * p.nc + j); ++emitted; }
-                        }
-                        kout[j] = k;
-                    }
-                } else {  // metrics.py:411-414: best class (first maximum)
-                    unsigned long long k = none;
-                    if (pass) {
-                        float best = x[5];
-                        int bj = 0;
-                        if (p.compat) best = __fmul_rn(best, obj);
-                        for (int j = 1; j < p.nc; ++j) {
-                            float cp = x[5 + j];
-                            if (p.compat) cp = __fmul_rn(cp, obj);
-                            if (cp > best) { best = cp; bj = j; }
-                        }
-                        if (best > p.conf && class_pass(p, p.compat ? (float)bj : best)) { k = key_of(p.compat ? best : obj, r * p.nc + bj); ++emitted; }
-                    }
-                    kout[0] = k;
-                }
-            } else {  // nc == 1 (metrics.py:415-419): row [cx,cy,w,h,obj,0]; nc == 0 in fixed mode
-                unsigned long long k = none;
-                if (pass && class_pass(p, 0.0f)) { k = key_of(obj, r); ++emitted; }
-                kout[0] = k;
-            }
-        }
         const int b0 = __shfl_sync(0xffffffffu, b, 0);
-        if (__all_sync(0xffffffffu, b == b0)) {
-            int tot = emitted;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-            if (lane == 0 && tot > 0 && b0 >= 0) atomicAdd(count + b0, tot);
-        } else if (emitted > 0) {
-            atomicAdd(count + b, emitted);
+        const bool uni = __all_sync(0xffffffffu, b == b0);
+        // whole block inside one image (all but the few blocks that straddle an image boundary): ONE position atomic per block
+        const long i_first = i - threadIdx.x;
+        const bool blk_uni = !p.multi_label && i_first + blockDim.x <= nbox && i_first / p.N == (i_first + blockDim.x - 1) / p.N;
+        // called by the whole warp: lanes with ok append `key` to the segment of their image
+        // (also accumulates, per image, the OR of the emitted score bits and of their complements: the bits all scores share)
+        auto emit = [&](bool ok, unsigned long long key) {
+            const unsigned int sb = (unsigned int)(key >> p.slot_bits);
+            if (blk_uni) {  // (a contended same-address atomic WITH a return value per warp cost 0.09 ms per step)
+                __shared__ int w_cnt[32];
+                __shared__ unsigned int w_or_s[32], w_nor_s[32];
+                __shared__ int blk_base;
+                const unsigned int m = __ballot_sync(0xffffffffu, ok);
+                const unsigned int w_or = __reduce_or_sync(0xffffffffu, ok ? sb : 0u), w_nor = __reduce_or_sync(0xffffffffu, ok ? ~sb : 0u);
+                const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+                if (lane == 0) { w_cnt[wid] = __popc(m); w_or_s[wid] = w_or; w_nor_s[wid] = w_nor; }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    int tot = 0;
+                    unsigned int bo = 0, bn = 0;
+                    for (int w = 0; w < nw; ++w) { tot += w_cnt[w]; bo |= w_or_s[w]; bn |= w_nor_s[w]; }
+                    blk_base = tot ? atomicAdd(count + b0, tot) : 0;
+                    if (bo & ~__ldcg(bits_or + b0)) atomicOr(bits_or + b0, bo);
+                    if (bn & ~__ldcg(bits_nor + b0)) atomicOr(bits_nor + b0, bn);
+                }
+                __syncthreads();
+                if (ok) {
+                    int off = blk_base;
+                    for (int w = 0; w < wid; ++w) off += w_cnt[w];
+                    keys[(long)b0 * stride + off + __popc(m & ((1u << lane) - 1u))] = key;
+                }
+                __syncthreads();  // the staging arrays are reused by the next grid-stride iteration
+            } else if (uni) {
+                const unsigned int m = __ballot_sync(0xffffffffu, ok);
+                if (m) {
+                    const unsigned int w_or = __reduce_or_sync(0xffffffffu, ok ? sb : 0u), w_nor = __reduce_or_sync(0xffffffffu, ok ? ~sb : 0u);
+                    int base = 0;
+                    if (lane == 0) {
+                        base = atomicAdd(count + b0, __popc(m));
+                        // the two masks saturate after a few warps: look before paying for the atomic (a stale read only costs a redundant one)
+                        if (w_or & ~__ldcg(bits_or + b0)) atomicOr(bits_or + b0, w_or);
+                        if (w_nor & ~__ldcg(bits_nor + b0)) atomicOr(bits_nor + b0, w_nor);
+                    }
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (ok) keys[(long)b0 * stride + base + __popc(m & ((1u << lane) - 1u))] = key;
+                }
+            } else if (ok) {
+                keys[(long)b * stride + atomicAdd(count + b, 1)] = key;
+                atomicOr(bits_or + b, sb);
+                atomicOr(bits_nor + b, ~sb);
+            }
+        };
+        const int r = inb ? (int)(i % p.N) : 0;
+        const float* x = p.pred + (inb ? i : 0) * p.no;
+        const float obj = inb ? x[4] : 0.0f;
+        const bool pass = inb && obj > p.conf;  // metrics.py:391,402
+        auto key_of = [&](float score, int slot) { return ((unsigned long long)desc_bits(score) << p.slot_bits) | (unsigned long long)slot; };
+        if (p.nc > 1 || (p.compat == 1 && p.nc == 1)) {
+            if (p.multi_label) {  // metrics.py:407-410: one row per (box, class) above the threshold
+                for (int j = 0; j < p.nc; ++j) {
+                    bool ok = false;
+                    unsigned long long k = 0;
+                    if (pass) {
+                        const float cp = x[5 + j];
+                        const float conf = p.compat ? __fmul_rn(cp, obj) : cp;
+                        if (conf > p.conf && class_pass(p, p.compat ? (float)j : cp)) { k = key_of(p.compat ? conf : obj, r * p.nc + j); ok = true; }
+                    }
+                    emit(ok, k);
+                }
+            } else {  // metrics.py:411-414: best class (first maximum)
+                bool ok = false;
+                unsigned long long k = 0;
+                if (pass) {
+                    float best = x[5];
+                    int bj = 0;
+                    if (p.compat) best = __fmul_rn(best, obj);
+                    for (int j = 1; j < p.nc; ++j) {
+                        float cp = x[5 + j];
+                        if (p.compat) cp = __fmul_rn(cp, obj);
+                        if (cp > best) { best = cp; bj = j; }
+                    }
+                    if (best > p.conf && class_pass(p, p.compat ? (float)bj : best)) { k = key_of(p.compat ? best : obj, r * p.nc + bj); ok = true; }
+                }
+                emit(ok, k);
+            }
+        } else {  // nc == 1 (metrics.py:415-419): row [cx,cy,w,h,obj,0]; nc == 0 in fixed mode
+            const bool ok = pass && class_pass(p, 0.0f);
+            emit(ok, ok ? key_of(obj, r) : 0ULL);
         }
     }
 }
@@ -252,34 +539,50 @@ __device__ __forceinline__ void load_cand(const BatchedParams& p, int b, unsigne
 // tests it performed (phase A: candidate vs kept box; phase B1: survivor vs earlier survivor of the chunk) to this counter.
 static unsigned long long* g_nms_pair_counter = nullptr;
 
-// grid = B images, 512 threads. Sorted keys of image b are the segment [off_b, off_b + cnt_b).
+// grid = B images, 512 threads.  The (unordered) keys of image b are keys[b * stride, b * stride + count[b]); they are consumed
+// in ascending order, up to SORT_KS per round (cta_next_sorted_batch), until max_det boxes are kept or 30 000 were walked.
 template <bool COUNT>
 __global__ void __launch_bounds__(NMS_THREADS)
-nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict__ keys, const int* __restrict__ count,
-                    float* __restrict__ out, int* __restrict__ out_count, unsigned long long* __restrict__ pair_counter) {
+nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict__ keys, long stride, const int* __restrict__ count,
+                    const unsigned int* __restrict__ bits_or, const unsigned int* __restrict__ bits_nor, float* __restrict__ out,
+                    int* __restrict__ out_count, unsigned long long* __restrict__ pair_counter) {
     __shared__ float kx1[NMS_MAX_KEEP], ky1[NMS_MAX_KEEP], kx2[NMS_MAX_KEEP], ky2[NMS_MAX_KEEP], kar[NMS_MAX_KEEP];
     __shared__ int surv[NMS_THREADS];   // chunk-local ids of phase-A survivors, in order
     __shared__ int warp_cnt[NMS_THREADS / 32];
     __shared__ int s_nsurv, s_kept;
     __shared__ float cx1[NMS_THREADS], cy1[NMS_THREADS], cx2[NMS_THREADS], cy2[NMS_THREADS], car[NMS_THREADS];
     __shared__ float crow[NMS_THREADS][7];
-    extern __shared__ unsigned int smask[];  // [NMS_THREADS][NMS_THREADS / 32] pairwise suppression bits of a chunk (32 KB)
+    extern __shared__ __align__(16) unsigned int smask[];  // [NMS_THREADS][NMS_THREADS / 32] pairwise suppression bits of a chunk (32 KB)
+    unsigned long long* skeys = reinterpret_cast<unsigned long long*>(smask + NMS_THREADS * (NMS_THREADS / 32));  // the round's sorted keys (64 KB)
+    SortScratch& S = *reinterpret_cast<SortScratch*>(skeys + SORT_KS);
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // frame-coordinate shift of this image's rows: columns (0, 1) of the reference rows [cx, cy, w, h, ...], columns
     // (0, 1, 2, 3) of the fixed rows [x1, y1, x2, y2, ...]
-    float shift = 0.0f;
-    if (p.tile_xy && lane < (p.compat ? 4 : 2)) shift = (float)p.tile_xy[2 * b + (lane & 1)];
+    const float shift_x = p.tile_xy ? (float)p.tile_xy[2 * b] : 0.0f, shift_y = p.tile_xy ? (float)p.tile_xy[2 * b + 1] : 0.0f;
+    const int shift_cols = p.tile_xy ? (p.compat ? 4 : 2) : 0;
     float* out_b = out + (long)b * p.out_rows * 7;
-    long off = 0;
-    for (int i = 0; i < b; ++i) off += count[i];
-    int n = count[b];
-    if (n > MAX_NMS_BOXES) n = MAX_NMS_BOXES;  // metrics.py:431-432 (sorted order => top-30000 by score)
+    const unsigned long long* gkeys = keys + (long)b * stride;
+    const int n_all = count[b];
+    const int n_cap = n_all > MAX_NMS_BOXES ? MAX_NMS_BOXES : n_all;  // metrics.py:431-432 (ascending key order => top-30000 by score)
     if (tid == 0) s_kept = 0;
     __syncthreads();
     unsigned int n_pairs = 0;
+    int consumed = 0;
+    bool have_lo = false;
+    unsigned long long lo = 0;
+    const unsigned int v_or = bits_or[b], v_and = ~bits_nor[b];
+    const int common_bits = __clz((int)(v_or ^ v_and));  // leading score bits all of this image's keys share
+    const unsigned long long common = common_bits ? (unsigned long long)(v_or >> (32 - common_bits)) : 0ULL;
 
+    while (consumed < n_cap && s_kept < p.max_det) {
+    const int m_batch = cta_next_sorted_batch(gkeys, n_all, have_lo, lo, n_all - consumed, min(SORT_KS, n_cap - consumed), 32 + p.slot_bits,
+                                              common_bits, common, skeys, S);
+    const int n = min(m_batch, n_cap - consumed);  // the batch may run past the 30 000-candidate cap: the tail is not walked
+    lo = skeys[n - 1];
+    have_lo = true;
+    consumed += n;
     for (int base = 0; base < n; base += NMS_THREADS) {
         const int kept0 = s_kept;
         if (kept0 >= p.max_det) break;
@@ -287,7 +590,7 @@ nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict_
         bool alive = i < n;
         Cand c;
         if (alive) {
-            load_cand(p, b, keys[off + i], c);
+            load_cand(p, b, skeys[i], c);
             // phase A: against everything kept in earlier chunks (parallel over candidates)
             // (a zero intersection gives an overlap of 0 or NaN, never > thr for thr >= 0: the division is skipped for disjoint
             // boxes, which is most of a dense scene's kept list -- 4.3 -> see profiles/r2c_nms_stress.md)
@@ -338,25 +641,48 @@ nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict_
             }
         }
         __syncthreads();
-        // phase B2: greedy resolution in order by one warp: lane w holds word w of the set kept within this chunk
+        // phase B2: greedy resolution in order by one warp, 32 survivors (one mask row per lane) at a time.  Lane w holds word w
+        // of the set kept within this chunk.  Suppression by survivors kept in EARLIER groups is tested by all lanes in
+        // parallel; only the in-group order is sequential, and that runs on registers (one ballot per survivor) -- the
+        // one-survivor-per-iteration form paid a shared-memory round trip per survivor (~30 000 cycles per full chunk).
         if (warp == 0) {
             const int ns = s_nsurv;
             int kept = kept0;
             unsigned int kw = 0;
-            for (int s = 0; s < ns && kept < p.max_det; ++s) {
-                const unsigned int m = lane <= (s >> 5) ? smask[s * (NMS_THREADS / 32) + lane] : 0u;
-                if (!__any_sync(0xffffffffu, (m & kw) != 0u)) {
-                    const int t = surv[s];
-                    if (lane == 0) { kx1[kept] = cx1[t]; ky1[kept] = cy1[t]; kx2[kept] = cx2[t]; ky2[kept] = cy2[t]; kar[kept] = car[t]; }
-                    if (lane < 7) out_b[kept * 7 + lane] = __fadd_rn(crow[t][lane], shift);
-                    if (lane == (s >> 5)) kw |= 1u << (s & 31);
-                    ++kept;
+            const int ngroups = (ns + 31) >> 5;
+            for (int G = 0; G < ngroups && kept < p.max_det; ++G) {
+                const int s = G * 32 + lane;
+                const bool valid = s < ns;
+                const unsigned int* mrow = smask + (valid ? s : 0) * (NMS_THREADS / 32);
+                bool dead = !valid;
+                for (int w = 0; w < G; ++w) {
+                    const unsigned int kww = __shfl_sync(0xffffffffu, kw, w);
+                    if (valid && (mrow[w] & kww) != 0u) dead = true;
                 }
+                const unsigned int diag = valid ? mrow[G] : 0u;  // earlier survivors of this group that overlap survivor s
+                unsigned int kg = 0;
+                int cnt = 0;
+                const int nt = min(32, ns - G * 32);
+                for (int t = 0; t < nt; ++t) {
+                    const bool alive_t = lane == t && !dead && (diag & kg) == 0u && kept + cnt < p.max_det;
+                    if (__ballot_sync(0xffffffffu, alive_t)) { kg |= 1u << t; ++cnt; }
+                }
+                if ((kg >> lane) & 1u) {  // the group's kept survivors append to the kept list and to the output, in order
+                    const int pos = kept + __popc(kg & ((1u << lane) - 1u));
+                    const int t = surv[s];
+                    kx1[pos] = cx1[t]; ky1[pos] = cy1[t]; kx2[pos] = cx2[t]; ky2[pos] = cy2[t]; kar[pos] = car[t];
+#pragma unroll
+                    for (int q = 0; q < 7; ++q) out_b[pos * 7 + q] = __fadd_rn(crow[t][q], q < shift_cols ? ((q & 1) ? shift_y : shift_x) : 0.0f);
+                }
+                if (lane == G) kw = kg;
+                kept += cnt;
             }
             __syncwarp();
             if (lane == 0) s_kept = kept;
         }
         __syncthreads();
+    }
+    __syncthreads();  // s_kept and skeys[n - 1] have been read by everyone before the next round overwrites the batch
     }
     if (tid == 0) out_count[b] = s_kept;
     if (COUNT) {
@@ -371,25 +697,19 @@ nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict_
 }
 
 struct BatchedWs {
-    unsigned long long* keys_in;
-    unsigned long long* keys_out;
-    unsigned int* total;
-    int* count;
-    void* cub_tmp;
-    size_t cub_bytes;
+    unsigned long long* keys;
+    int* count;              // [B] candidates per image, then [B] OR of their score bits, [B] OR of the complements (one memset)
+    unsigned int* bits_or;
+    unsigned int* bits_nor;
 };
 static size_t batched_layout(int B, int N, int nc, int multi_label, void* base, BatchedWs* ws) {
     const size_t cap = (size_t)B * N * ((multi_label && nc > 1) ? nc : 1);
-    size_t cub_bytes = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (long)cap);
     size_t off = 0;
     uint8_t* b = (uint8_t*)base;
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return b ? (void*)(b + o) : nullptr; };
     void* k0 = take(8 * cap);
-    void* k1 = take(8 * cap);
-    void* cnt = take(sizeof(int) * (B + 1));
-    void* c = take(cub_bytes);
-    if (ws) { ws->keys_in = (unsigned long long*)k0; ws->keys_out = (unsigned long long*)k1; ws->count = (int*)cnt + 1; ws->total = (unsigned int*)cnt; ws->cub_tmp = c; ws->cub_bytes = cub_bytes; }
+    void* cnt = take(sizeof(int) * 3 * B);
+    if (ws) { ws->keys = (unsigned long long*)k0; ws->count = (int*)cnt; ws->bits_or = (unsigned int*)cnt + B; ws->bits_nor = (unsigned int*)cnt + 2 * B; }
     return off + 256;
 }
 
@@ -414,10 +734,10 @@ extern "C" int skb_nms_f32(const float* boxes, const float* scores, int32_t n, f
     NmsWs ws;
     nms_layout(n, workspace, &ws);
     const int cbk = (n + 63) / 64;
-    iota_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws.idx_in, n);
-    SKB_LAUNCH_CHECK();
-    SKB_CUDA(cub::DeviceRadixSort::SortPairsDescending(ws.cub_tmp, ws.cub_bytes, scores, ws.keys_out, ws.idx_in, ws.idx_out, n, 0, 32, st));
-    gather_boxes_kernel<<<(n + 255) / 256, 256, 0, st>>>((const float4*)boxes, ws.idx_out, n, ws.sboxes);
+    constexpr int kSortBytes = SORT_KS * 8 + (int)sizeof(SortScratch);
+    static PerDeviceOnce order_once;
+    if (order_once.first()) SKB_CUDA(cudaFuncSetAttribute(nms_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortBytes));
+    nms_order_kernel<<<1, NMS_THREADS, kSortBytes, st>>>((const float4*)boxes, scores, n, ws.keys, ws.idx_out, ws.sboxes);
     SKB_LAUNCH_CHECK();
     nms_mask_kernel<<<dim3(cbk, cbk), 64, 0, st>>>(ws.sboxes, n, iou_thr, cbk, ws.mask);
     SKB_LAUNCH_CHECK();
@@ -471,12 +791,10 @@ static int nms_batched_impl(const float* pred, int32_t b, int32_t n, int32_t nc,
     SKB_REQUIRE(iou_thr >= 0.0f && iou_thr <= 1.0f && conf_thr >= 0.0f && conf_thr <= 1.0f, SKB_ERR_ARG,
                 "nms_batched: thresholds must lie in [0, 1] (metrics.py:386-387), got conf %g iou %g", (double)conf_thr, (double)iou_thr);
     SKB_REQUIRE(max_det >= 1 && max_det <= NMS_MAX_KEEP, SKB_ERR_UNSUPPORTED, "nms_batched: max_det=%d (supported: 1..%d)", max_det, NMS_MAX_KEEP);
-    int slot_bits = 1, img_bits = 1;
+    int slot_bits = 1;
     while ((1L << slot_bits) < (long)n * (nc > 1 ? nc : 1)) ++slot_bits;
-    while ((1 << img_bits) < b) ++img_bits;
-    SKB_REQUIRE(slot_bits <= KEY_MAX_SLOT_BITS && slot_bits + img_bits <= 32, SKB_ERR_UNSUPPORTED,
-                "nms_batched: B=%d N*nc=%ld exceed the 64-bit sort key (image %d + slot %d bits > 32)", b, (long)n * (nc > 1 ? nc : 1),
-                img_bits, slot_bits);
+    SKB_REQUIRE(slot_bits <= KEY_MAX_SLOT_BITS, SKB_ERR_UNSUPPORTED, "nms_batched: N*nc=%ld exceeds the %d-bit slot field of the sort key",
+                (long)n * (nc > 1 ? nc : 1), KEY_MAX_SLOT_BITS);
     SKB_REQUIRE(n_classes <= 32, SKB_ERR_UNSUPPORTED, "nms_batched: at most 32 class filters");
     multi_label = (multi_label && nc > 1) ? 1 : 0;  // metrics.py:396
     SKB_REQUIRE(workspace_bytes >= skb_nms_batched_workspace_bytes(b, n, nc, multi_label), SKB_ERR_WORKSPACE, "nms_batched: workspace too small");
@@ -484,7 +802,7 @@ static int nms_batched_impl(const float* pred, int32_t b, int32_t n, int32_t nc,
     batched_layout(b, n, nc, multi_label, workspace, &ws);
     const size_t cap = (size_t)b * n * (multi_label ? nc : 1);
     cudaStream_t st = (cudaStream_t)stream;
-    SKB_CUDA(cudaMemsetAsync(ws.total, 0, sizeof(int) * (b + 1), st));
+    SKB_CUDA(cudaMemsetAsync(ws.count, 0, sizeof(int) * 3 * b, st));
     FilterParams fp;
     memset(&fp, 0, sizeof(fp));
     fp.pred = pred; fp.B = b; fp.N = n; fp.nc = nc; fp.no = nc + 5; fp.conf = conf_thr; fp.multi_label = multi_label; fp.compat = compat;
@@ -494,21 +812,23 @@ static int nms_batched_impl(const float* pred, int32_t b, int32_t n, int32_t nc,
     const long nbox = (long)b * n;
     long g = (nbox + 255) / 256;
     const long gcap = (long)num_sms() * 16;
-    nms_filter_kernel<<<(int)(g > gcap ? gcap : g), 256, 0, st>>>(fp, ws.keys_in, ws.count);
+    const long stride = (long)n * (multi_label ? nc : 1);  // key segment per image
+    nms_filter_kernel<<<(int)(g > gcap ? gcap : g), 256, 0, st>>>(fp, ws.keys, ws.count, stride, ws.bits_or, ws.bits_nor);
     SKB_LAUNCH_CHECK();
-    SKB_CUDA(cub::DeviceRadixSort::SortKeys(ws.cub_tmp, ws.cub_bytes, ws.keys_in, ws.keys_out, (long)cap, 0, 32 + slot_bits + img_bits, st));
     BatchedParams bp;
     bp.pred = pred; bp.B = b; bp.N = n; bp.nc = nc; bp.no = nc + 5; bp.iou = iou_thr; bp.agnostic = agnostic; bp.multi_label = multi_label;
     bp.compat = compat; bp.max_det = max_det; bp.capacity = (int)cap; bp.slot_bits = slot_bits;
     bp.tile_xy = tile_xy_dev; bp.out_rows = out_rows;
-    constexpr int kMaskBytes = NMS_THREADS * (NMS_THREADS / 32) * (int)sizeof(unsigned int);
+    constexpr int kMaskBytes = NMS_THREADS * (NMS_THREADS / 32) * (int)sizeof(unsigned int) + SORT_KS * 8 + (int)sizeof(SortScratch);
     static PerDeviceOnce attr_once;
     if (attr_once.first()) {
         SKB_CUDA(cudaFuncSetAttribute(nms_keptlist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaskBytes));
         SKB_CUDA(cudaFuncSetAttribute(nms_keptlist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaskBytes));
     }
-    if (g_nms_pair_counter) nms_keptlist_kernel<true><<<b, NMS_THREADS, kMaskBytes, st>>>(bp, ws.keys_out, ws.count, out, out_count, g_nms_pair_counter);
-    else nms_keptlist_kernel<false><<<b, NMS_THREADS, kMaskBytes, st>>>(bp, ws.keys_out, ws.count, out, out_count, nullptr);
+    if (g_nms_pair_counter)
+        nms_keptlist_kernel<true><<<b, NMS_THREADS, kMaskBytes, st>>>(bp, ws.keys, stride, ws.count, ws.bits_or, ws.bits_nor, out, out_count, g_nms_pair_counter);
+    else
+        nms_keptlist_kernel<false><<<b, NMS_THREADS, kMaskBytes, st>>>(bp, ws.keys, stride, ws.count, ws.bits_or, ws.bits_nor, out, out_count, nullptr);
     SKB_LAUNCH_CHECK();
     return SKB_OK;
 }

@@ -48,7 +48,7 @@ def test_version_and_error_string_without_gpu(native):
 def test_workspace_queries_are_pure_host_functions(native):
     L = native.lib()
     assert L.skb_nms_workspace_bytes(30000) > 30000 * 469 * 8
-    assert L.skb_nms_batched_workspace_bytes(64, 50000, 10, 0) >= 2 * 8 * 64 * 50000
+    assert L.skb_nms_batched_workspace_bytes(64, 50000, 10, 0) >= 8 * 64 * 50000      # one 64-bit key per candidate box (no sort double buffer)
     assert L.skb_cbam_workspace_bytes(16, 80, 80, 512) > 0
     assert L.skb_cla_workspace_bytes(16, 160, 160, 4) >= 16 * 4 * 160 * 160 * 4
 
