@@ -579,4 +579,12 @@ def make_calibrated_state_dict(cfg, seed: int = 0, calib_batch: int = 8, calib_h
             sd[k] = sd[k] * RESIDUAL_GAMMA
     g = np.random.Generator(np.random.PCG64([calib_seed, seed]))
     x = torch.from_numpy(g.integers(0, 256, (calib_batch, 3, *calib_hw), dtype=np.uint8)).float() / 255.0
-    return calibrate_bn(sd, cfg, x)
+    # ONE host thread: the calibration pass is fp32 CPU arithmetic whose summation order follows the thread count, and
+    # torchrun starts its ranks with OMP_NUM_THREADS=1 -- with the default thread count the weights (and so the detection
+    # checksum of bench.py's tiled leg) differed in the last bits between a plain run and a torchrun rank on the same box
+    nt = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        return calibrate_bn(sd, cfg, x)
+    finally:
+        torch.set_num_threads(nt)
