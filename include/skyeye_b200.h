@@ -189,6 +189,13 @@ int skb_nms_batched_f32(const float* pred, int32_t b, int32_t n, int32_t nc, flo
 int skb_nms_batched_tiles_f32(const float* pred, int32_t b, int32_t n, int32_t nc, float conf_thr, float iou_thr, int32_t agnostic,
                               int32_t multi_label, int32_t max_det, int32_t compat, const int32_t* tile_xy_dev, float* out_packed,
                               int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
+/* Correct-prediction matrix of validate()'s process_batch (skyeye/cli/validate.py:71-108, IoU as box_iou, skyeye/utils/metrics.py:17-44)
+ * for ONE image, on the device: labels fp32 [n_labels][5] = (cls, x1, y1, x2, y2), dets fp32 [n_dets][6] = (x1, y1, x2, y2, conf, cls),
+ * iouv fp32 [n_iou] thresholds (device), correct uint8 [n_dets][n_iou] (1 = the detection is its best same-class label's
+ * highest-IoU detection and that IoU >= the threshold).  Workspace: skb_match_workspace_bytes. */
+size_t skb_match_workspace_bytes(int32_t n_dets, int32_t n_labels);
+int skb_match_detections_f32(const float* labels, int32_t n_labels, const float* dets, int32_t n_dets, const float* iouv, int32_t n_iou,
+                             uint8_t* correct, void* workspace, size_t workspace_bytes, void* stream);
 /* Diagnostics only (no reference counterpart): counter_dev = device pointer of an unsigned 64-bit counter that receives the
  * number of IoU pair tests of every following skb_nms_batched*_f32 call (SURVEY.md §8d asks for pairs/s on config 5;
  * scripts/bench_nms_stress.py); NULL switches the counting kernel variant off. */

@@ -113,6 +113,8 @@ _SIGNATURES = {
     "skb_nms_batched_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_float, c_float, POINTER(c_int32), c_int32,
                                       c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "skb_debug_nms_pair_counter": (c_int32, [c_void_p]),
+    "skb_match_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "skb_match_detections_f32": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "skb_nms_batched_tiles_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_int32, c_int32, c_int32, c_int32,
                                             c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "skb_tile_merge_pred_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),

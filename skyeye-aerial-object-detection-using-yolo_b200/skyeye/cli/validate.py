@@ -77,6 +77,21 @@ def process_batch(detections, labels, iouv):
     """Correct-prediction matrix [n_det, n_iou] (validate.py:71-108): a detection is correct at threshold t if
     it is the best-IoU unmatched detection of a same-class label with IoU >= t; one label per detection and
     one detection per label, highest IoU first."""
+    if detections.is_cuda:  # the validation loop: one kernel, no host round trip (skb_match_detections_f32, csrc/eval.cu)
+        from .. import _native as N
+        n, m, T = detections.shape[0], labels.shape[0], iouv.shape[0]
+        out = torch.zeros((n, T), dtype=torch.uint8, device=detections.device)
+        if n == 0 or m == 0:
+            return out.bool()
+        det = detections[:, :6].float().contiguous()
+        lab = labels[:, :5].float().contiguous().to(det.device)
+        thr = iouv.float().contiguous().to(det.device)
+        ws = torch.empty(int(N.lib().skb_match_workspace_bytes(n, m)) + 256, dtype=torch.uint8, device=det.device)
+        with torch.cuda.device(det.device):
+            N.check(N.lib().skb_match_detections_f32(lab.data_ptr(), m, det.data_ptr(), n, thr.data_ptr(), T, out.data_ptr(), ws.data_ptr(),
+                                                     ws.numel(), torch.cuda.current_stream().cuda_stream), "skb_match_detections_f32")
+        return out.bool()
+    # host tensors (unit tests of the bookkeeping against the live reference): the reference's own sequence of torch / numpy steps
     correct = torch.zeros(detections.shape[0], iouv.shape[0], dtype=torch.bool, device=iouv.device)
     if detections.shape[0] == 0 or labels.shape[0] == 0:
         return correct

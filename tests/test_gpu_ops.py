@@ -262,3 +262,33 @@ def test_letterbox_gpu_matches_cv2_pipeline(hw, new):
         assert int(diff.max()) == 0
     else:
         assert int(diff.max()) <= 1 and float((diff > 0).mean()) < 5e-3
+
+
+@pytest.mark.parametrize("n,m,ncls,seed", [(300, 40, 10, 0), (1000, 500, 3, 1), (7, 1, 1, 2), (64, 200, 80, 3)])
+def test_match_detections_kernel_equals_the_reference_bookkeeping(n, m, ncls, seed):
+    """process_batch (validate.py:71-108) on the device vs its torch / numpy sequence on the host (which tests/test_eval_bookkeeping.py
+    checks against the live reference): the correct-prediction matrices must be identical."""
+    from skyeye.cli import validate as V
+    g = cases.rng("match", n, m, seed)
+    def boxes(k):
+        xy = g.random((k, 2), dtype=np.float32) * 600
+        wh = g.random((k, 2), dtype=np.float32) * 80 + 8
+        return np.concatenate((xy, xy + wh), 1)
+    lab_boxes = boxes(m)
+    labels = np.concatenate((g.integers(0, ncls, (m, 1)).astype(np.float32), lab_boxes), 1)
+    # detections: jittered copies of labels (so many pairs overlap strongly) + random boxes, random classes for a third of them
+    src = g.integers(0, m, n)
+    det_boxes = lab_boxes[src] + g.normal(0, 4.0, (n, 4)).astype(np.float32)
+    det_boxes[:, 2:] = np.maximum(det_boxes[:, 2:], det_boxes[:, :2] + 1)
+    cls = labels[src, 0].copy()
+    flip = g.random(n) < 0.33
+    cls[flip] = g.integers(0, ncls, int(flip.sum())).astype(np.float32)
+    det = np.concatenate((det_boxes, g.random((n, 1), dtype=np.float32), cls[:, None]), 1).astype(np.float32)
+    iouv = torch.linspace(0.5, 0.95, 10)
+    ref = V.process_batch(torch.from_numpy(det), torch.from_numpy(labels), iouv)
+    got = V.process_batch(torch.from_numpy(det).cuda(), torch.from_numpy(labels).cuda(), iouv.cuda()).cpu()
+    assert got.shape == ref.shape and got.dtype == torch.bool
+    assert torch.equal(got, ref), int((got != ref).sum())
+    assert int(ref.sum()) > 0
+    assert V.process_batch(torch.from_numpy(det[:0]).cuda(), torch.from_numpy(labels).cuda(), iouv.cuda()).shape == (0, 10)
+    assert not V.process_batch(torch.from_numpy(det).cuda(), torch.from_numpy(labels[:0]).cuda(), iouv.cuda()).any()
