@@ -220,6 +220,57 @@ __global__ void maxpool5_kernel(const __nv_bfloat16* __restrict__ x, long xpitch
     }
 }
 
+// SPP's three pools in ONE pass (blocks.py:143-149): a CTA owns the whole H x W map of 16 channels of one image (32 bytes per
+// pixel = one DRAM sector), reads it once into shared memory and runs the 5x5 cascade there (5, 9 = 5o5, 13 = 5o5o5: exact for
+// max with -inf padding), writing each stage's result to its concat slice.  The three chained launches above read and wrote
+// the map three times (1.6 TB/s); this reads it once and writes three slices.  Separable: row maxima into a temporary, column
+// maxima back.  Shared memory: 3 x H*W*32 B (154 KB at 40 x 40); larger maps keep the cascade of launches.
+__global__ void __launch_bounds__(256)
+spp_fused_kernel(const __nv_bfloat16* __restrict__ x, long xpitch, __nv_bfloat16* __restrict__ y5, __nv_bfloat16* __restrict__ y9,
+                 __nv_bfloat16* __restrict__ y13, long ypitch, int H, int W, int groups) {
+    extern __shared__ __align__(16) uint4 spp_smem[];
+    const int items = H * W * 2;  // 16-byte vectors: [y][x][2]
+    uint4* A = spp_smem;          // current stage input
+    uint4* T = A + items;         // row maxima
+    uint4* B = T + items;         // stage output
+    const int n = blockIdx.x / groups, cg = blockIdx.x - n * groups;
+    const long img = (long)n * H * W;
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const int pix = i >> 1, v = i & 1;
+        A[i] = *reinterpret_cast<const uint4*>(x + (img + pix) * xpitch + cg * 16 + v * 8);
+    }
+    __syncthreads();
+    auto vmax = [](uint4 a, const uint4& b) {
+        __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(&a);
+        const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pa[q] = __hmax2(pa[q], pb[q]);
+        return a;
+    };
+    __nv_bfloat16* outs[3] = {y5, y9, y13};
+#pragma unroll 1
+    for (int stage = 0; stage < 3; ++stage) {
+        for (int i = threadIdx.x; i < items; i += blockDim.x) {  // horizontal 5-max
+            const int pix = i >> 1, v = i & 1, py = pix / W, px = pix - py * W;
+            const int xa = max(px - 2, 0), xb = min(px + 2, W - 1);
+            uint4 m = A[(py * W + xa) * 2 + v];
+            for (int xx = xa + 1; xx <= xb; ++xx) m = vmax(m, A[(py * W + xx) * 2 + v]);
+            T[i] = m;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < items; i += blockDim.x) {  // vertical 5-max, store
+            const int pix = i >> 1, v = i & 1, py = pix / W, px = pix - py * W;
+            const int ya = max(py - 2, 0), yb = min(py + 2, H - 1);
+            uint4 m = T[(ya * W + px) * 2 + v];
+            for (int yy = ya + 1; yy <= yb; ++yy) m = vmax(m, T[(yy * W + px) * 2 + v]);
+            B[i] = m;
+            *reinterpret_cast<uint4*>(outs[stage] + (img + pix) * ypitch + cg * 16 + v * 8) = m;
+        }
+        __syncthreads();
+        uint4* t = A; A = B; B = t;  // the stage's output is the next stage's input
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // CBAM (attention.py:37-60, 80-98)
 // ---------------------------------------------------------------------------------------------
@@ -520,6 +571,135 @@ cla_apply_kernel(const float* __restrict__ s, const float* __restrict__ st, cons
     }
 }
 
+// ---- exact 2x ratio (H = 2 Hk, W = 2 Wk: every CLA call of the detector) -------------------------------------------------
+// With align_corners = False and scale 2 the source coordinate of output row y is y/2 - 0.25: output rows 2b-1 and 2b both
+// interpolate source rows (b-1, b), with weights (0.75, 0.25) and (0.25, 0.75); likewise for columns.  So the 2 x 2 output block
+// {2bi-1, 2bi} x {2bj-1, 2bj} needs exactly FOUR source pixels, which one thread loads and unpacks once (the generic kernels
+// load and unpack four source vectors per OUTPUT pixel: they are issue-bound at ~2 TB/s).  Border blocks (bi = 0 or Hk, bj = 0
+// or Wk) have one valid row / column and a clamped source index, where both source rows coincide and the weights do not matter.
+// Interpolation is separable (columns, then rows) in packed fp32x2 arithmetic.
+struct Blk2x {
+    int r0, r1, c0, c1;   // source rows / columns
+    int ya, yb, xa, xb;   // output rows 2bi-1, 2bi and columns 2bj-1, 2bj (ya / xa < 0 and yb >= H / xb >= W are skipped)
+};
+__device__ __forceinline__ Blk2x blk2x(int bi, int bj, int Hk, int Wk) {
+    Blk2x b;
+    b.r0 = max(bi - 1, 0); b.r1 = min(bi, Hk - 1); b.c0 = max(bj - 1, 0); b.c1 = min(bj, Wk - 1);
+    b.ya = 2 * bi - 1; b.yb = 2 * bi; b.xa = 2 * bj - 1; b.xb = 2 * bj;
+    return b;
+}
+// four source vectors (8 channels at `c`) -> the four interpolated vectors of the block: o[0] = (ya, xa), o[1] = (ya, xb), o[2] = (yb, xa), o[3] = (yb, xb)
+__device__ __forceinline__ void interp2x8(const __nv_bfloat16* __restrict__ t, long pitch, long img0, int Wk, const Blk2x& b, int c, float (&o)[4][8]) {
+    float s00[8], s01[8], s10[8], s11[8];
+    unpack8(*reinterpret_cast<const uint4*>(t + (img0 + (long)b.r0 * Wk + b.c0) * pitch + c), s00);
+    unpack8(*reinterpret_cast<const uint4*>(t + (img0 + (long)b.r0 * Wk + b.c1) * pitch + c), s01);
+    unpack8(*reinterpret_cast<const uint4*>(t + (img0 + (long)b.r1 * Wk + b.c0) * pitch + c), s10);
+    unpack8(*reinterpret_cast<const uint4*>(t + (img0 + (long)b.r1 * Wk + b.c1) * pitch + c), s11);
+    const float2 w75 = make_float2(0.75f, 0.75f), w25 = make_float2(0.25f, 0.25f);
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        const float2 a = make_float2(s00[j], s00[j + 1]), bb = make_float2(s01[j], s01[j + 1]);
+        const float2 cc = make_float2(s10[j], s10[j + 1]), d = make_float2(s11[j], s11[j + 1]);
+        const float2 ta = ffma2(w75, a, fmul2(w25, bb)), tb = ffma2(w25, a, fmul2(w75, bb));    // row r0 at columns xa, xb
+        const float2 ua = ffma2(w75, cc, fmul2(w25, d)), ub = ffma2(w25, cc, fmul2(w75, d));    // row r1 at columns xa, xb
+        const float2 o0 = ffma2(w75, ta, fmul2(w25, ua)), o1 = ffma2(w75, tb, fmul2(w25, ub));  // output row ya
+        const float2 o2 = ffma2(w25, ta, fmul2(w75, ua)), o3 = ffma2(w25, tb, fmul2(w75, ub));  // output row yb
+        o[0][j] = o0.x; o[0][j + 1] = o0.y; o[1][j] = o1.x; o[1][j + 1] = o1.y;
+        o[2][j] = o2.x; o[2][j + 1] = o2.y; o[3][j] = o3.x; o[3][j + 1] = o3.y;
+    }
+}
+// one CTA per block row bi of an image: scores of output rows 2bi-1, 2bi staged in shared memory ([2][heads][W]), coalesced stores
+__global__ void __launch_bounds__(256)
+cla_score2x_kernel(const __nv_bfloat16* __restrict__ q, long qpitch, const __nv_bfloat16* __restrict__ k, long kpitch,
+                   int N, int H, int W, int Hk, int Wk, int Cq, int heads, float scale, float* __restrict__ s) {
+    extern __shared__ float srow[];  // [2][heads][W]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int n = blockIdx.x / (Hk + 1), bi = blockIdx.x - n * (Hk + 1);
+    const int cph = Cq / heads, lph = cph >> 3;
+    const long kimg = (long)n * Hk * Wk, qimg = (long)n * H * W;
+    for (int bj = warp; bj <= Wk; bj += nwarp) {
+        const Blk2x b = blk2x(bi, bj, Hk, Wk);
+        const bool va = b.ya >= 0, vb = b.yb < H, ua = b.xa >= 0, ub = b.xb < W;
+        for (int cbase = 0; cbase < Cq; cbase += 256) {
+            const int c = cbase + lane * 8;
+            float part[4] = {0.f, 0.f, 0.f, 0.f};
+            if (c < Cq) {
+                float kv[4][8];
+                interp2x8(k, kpitch, kimg, Wk, b, c, kv);
+                const int ys[4] = {b.ya, b.ya, b.yb, b.yb}, xs[4] = {b.xa, b.xb, b.xa, b.xb};
+                const bool ok[4] = {va && ua, va && ub, vb && ua, vb && ub};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (ok[t]) {
+                        float qv[8];
+                        unpack8(*reinterpret_cast<const uint4*>(q + (qimg + (long)ys[t] * W + xs[t]) * qpitch + c), qv);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) part[t] += qv[j] * kv[t][j];
+                    }
+                }
+            }
+            for (int o = lph >> 1; o > 0; o >>= 1) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) part[t] += __shfl_xor_sync(0xffffffffu, part[t], o);
+            }
+            if (c < Cq && (lane & (lph - 1)) == 0) {
+                const int g = c / cph;
+                if (va && ua) srow[(0 * heads + g) * W + b.xa] = part[0] * scale;
+                if (va && ub) srow[(0 * heads + g) * W + b.xb] = part[1] * scale;
+                if (vb && ua) srow[(1 * heads + g) * W + b.xa] = part[2] * scale;
+                if (vb && ub) srow[(1 * heads + g) * W + b.xb] = part[3] * scale;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * heads * W; i += blockDim.x) {
+        const int r = i / (heads * W), rem = i - r * heads * W, g = rem / W, x = rem - g * W;
+        const int y = 2 * bi - 1 + r;
+        if (y >= 0 && y < H) s[(((long)n * heads + g) * H + y) * W + x] = srow[i];
+    }
+}
+__global__ void __launch_bounds__(256)
+cla_apply2x_kernel(const float* __restrict__ s, const float* __restrict__ st, const __nv_bfloat16* __restrict__ v, long vpitch,
+                   int N, int H, int W, int Hk, int Wk, int Cv, int heads, float r2, __nv_bfloat16* __restrict__ o, long opitch) {
+    extern __shared__ float arow[];  // [2][heads][W]: attention weights of output rows 2bi-1, 2bi
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int n = blockIdx.x / (Hk + 1), bi = blockIdx.x - n * (Hk + 1);
+    for (int i = threadIdx.x; i < 2 * heads * W; i += blockDim.x) {
+        const int r = i / (heads * W), rem = i - r * heads * W, g = rem / W, x = rem - g * W;
+        const int y = 2 * bi - 1 + r;
+        float a = 0.f;
+        if (y >= 0 && y < H) {
+            const long ng = (long)n * heads + g;
+            const float2 ms = *reinterpret_cast<const float2*>(st + (ng * W + x) * 2);
+            a = r2 * expf(s[(ng * H + y) * W + x] - ms.x) * ms.y;
+        }
+        arow[i] = a;
+    }
+    __syncthreads();
+    const int cph = Cv / heads;
+    const long vimg = (long)n * Hk * Wk, oimg = (long)n * H * W;
+    for (int bj = warp; bj <= Wk; bj += nwarp) {
+        const Blk2x b = blk2x(bi, bj, Hk, Wk);
+        const bool va = b.ya >= 0, vb = b.yb < H, ua = b.xa >= 0, ub = b.xb < W;
+        for (int c = lane * 8; c < Cv; c += 256) {
+            float ov[4][8];
+            interp2x8(v, vpitch, vimg, Wk, b, c, ov);
+            const int g = c / cph;
+            const int ys[4] = {b.ya, b.ya, b.yb, b.yb}, xs[4] = {b.xa, b.xb, b.xa, b.xb};
+            const bool ok[4] = {va && ua, va && ub, vb && ua, vb && ub};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                if (ok[t]) {
+                    const float w = arow[((t >> 1) * heads + g) * W + xs[t]];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) ov[t][j] *= w;
+                    *reinterpret_cast<uint4*>(o + (oimg + (long)ys[t] * W + xs[t]) * opitch + c) = pack8(ov[t]);
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // LayerNorm over channels: one warp per token, VPL 16-byte vectors per lane (C = 256 * VPL, or less
 // with idle lanes), TPI tokens in flight per warp so that 4 independent loads per lane are
@@ -664,6 +844,27 @@ extern "C" int skb_maxpool5_bf16(const skb_view* x, const skb_view* y, void* str
     return SKB_OK;
 }
 
+// the three SPP pools of x (blocks.py:143-149) in one pass; all four views [n, h, w, c] with the same pixel pitch family
+extern "C" int skb_spp_pools_bf16(const skb_view* x, const skb_view* y5, const skb_view* y9, const skb_view* y13, void* stream) {
+    int rc = check_device();
+    if (rc != SKB_OK) return rc;
+    SKB_REQUIRE(view_ok_bf16(x) && view_ok_bf16(y5) && view_ok_bf16(y9) && view_ok_bf16(y13), SKB_ERR_ARG, "spp_pools: bad view");
+    const skb_view* ys[3] = {y5, y9, y13};
+    for (int i = 0; i < 3; ++i)
+        SKB_REQUIRE(ys[i]->n == x->n && ys[i]->h == x->h && ys[i]->w == x->w && ys[i]->c == x->c && ys[i]->pitch == y5->pitch, SKB_ERR_ARG,
+                    "spp_pools: output %d does not match the input map", i);
+    SKB_REQUIRE(x->c % 16 == 0, SKB_ERR_UNSUPPORTED, "spp_pools: C=%d must be a multiple of 16", x->c);
+    const size_t smem = (size_t)3 * x->h * x->w * 32;
+    SKB_REQUIRE(smem <= 200 * 1024, SKB_ERR_UNSUPPORTED, "spp_pools: %dx%d map needs %zu bytes of shared memory (use skb_maxpool5_bf16 x 3)", x->h, x->w, smem);
+    static PerDeviceOnce once;
+    if (once.first()) SKB_CUDA(cudaFuncSetAttribute(spp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const int groups = x->c / 16;
+    spp_fused_kernel<<<x->n * groups, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x->ptr, x->pitch, (__nv_bfloat16*)y5->ptr,
+                                                                         (__nv_bfloat16*)y9->ptr, (__nv_bfloat16*)y13->ptr, y5->pitch, x->h, x->w, groups);
+    SKB_LAUNCH_CHECK();
+    return SKB_OK;
+}
+
 static int cbam_slabs(int hw) { int s = (hw + 255) / 256; return s < 1 ? 1 : (s > 64 ? 64 : s); }
 
 extern "C" size_t skb_cbam_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t c) {
@@ -725,13 +926,26 @@ extern "C" int skb_cla_core_bf16(const skb_view* q, const skb_view* k, const skb
     const long npix = (long)N * H * W;
     const size_t row_sh = sizeof(float) * (size_t)heads * W;
     SKB_REQUIRE(row_sh <= 48 * 1024, SKB_ERR_UNSUPPORTED, "cla: heads*W = %d too large for the row staging buffer", heads * W);
-    cla_score_kernel<<<N * H, 256, row_sh, cs>>>((const __nv_bfloat16*)q->ptr, q->pitch, (const __nv_bfloat16*)k->ptr, k->pitch, N, H, W,
-                                                 k->h, k->w, q->c, heads, scale, s);
+    static int cla2x = -1;  // tuning knob (not part of the ABI): SKB_CLA_2X=0 keeps the generic bilinear kernels
+    if (cla2x < 0) { const char* e = getenv("SKB_CLA_2X"); cla2x = e ? atoi(e) : 1; }
+    const bool exact2x = cla2x && H == 2 * k->h && W == 2 * k->w && 2 * row_sh <= 48 * 1024;
+    if (exact2x) {
+        cla_score2x_kernel<<<N * (k->h + 1), 256, 2 * row_sh, cs>>>((const __nv_bfloat16*)q->ptr, q->pitch, (const __nv_bfloat16*)k->ptr, k->pitch,
+                                                                    N, H, W, k->h, k->w, q->c, heads, scale, s);
+    } else {
+        cla_score_kernel<<<N * H, 256, row_sh, cs>>>((const __nv_bfloat16*)q->ptr, q->pitch, (const __nv_bfloat16*)k->ptr, k->pitch, N, H, W,
+                                                     k->h, k->w, q->c, heads, scale, s);
+    }
     SKB_LAUNCH_CHECK();
     cla_colstat_kernel<<<N * heads * ((W + 31) / 32), 256, 0, cs>>>(s, N * heads, H, W, st);
     SKB_LAUNCH_CHECK();
-    cla_apply_kernel<<<N * H, 256, row_sh, cs>>>(s, st, (const __nv_bfloat16*)v->ptr, v->pitch, N, H, W, v->h, v->w, v->c, heads, r2,
-                                                 (__nv_bfloat16*)o->ptr, o->pitch);
+    if (exact2x) {
+        cla_apply2x_kernel<<<N * (k->h + 1), 256, 2 * row_sh, cs>>>(s, st, (const __nv_bfloat16*)v->ptr, v->pitch, N, H, W, v->h, v->w, v->c, heads, r2,
+                                                                    (__nv_bfloat16*)o->ptr, o->pitch);
+    } else {
+        cla_apply_kernel<<<N * H, 256, row_sh, cs>>>(s, st, (const __nv_bfloat16*)v->ptr, v->pitch, N, H, W, v->h, v->w, v->c, heads, r2,
+                                                     (__nv_bfloat16*)o->ptr, o->pitch);
+    }
     SKB_LAUNCH_CHECK();
     return SKB_OK;
 }

@@ -93,6 +93,7 @@ _SIGNATURES = {
     "skb_letterbox_u8": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                    c_int32, c_void_p]),
     "skb_maxpool5_bf16": (c_int32, [POINTER(skb_view), POINTER(skb_view), c_void_p]),
+    "skb_spp_pools_bf16": (c_int32, [POINTER(skb_view), POINTER(skb_view), POINTER(skb_view), POINTER(skb_view), c_void_p]),
     "skb_cbam_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "skb_cbam_bf16": (c_int32, [POINTER(skb_view), c_void_p, c_void_p, c_int32, c_void_p, POINTER(skb_view),
                                 c_void_p, c_size_t, c_void_p]),

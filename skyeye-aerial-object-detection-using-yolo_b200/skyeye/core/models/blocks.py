@@ -103,10 +103,15 @@ class SPPBlock(nn.Module):
         h = self.hidden
         cat = plan.buf(x.n, x.h, x.w, 4 * h)
         self.cv1.lower(plan, x, cat.slice(0, h), name=name + ".cv1")
-        for i in range(3):  # mp9 = mp5(mp5), mp13 = mp5(mp5(mp5)) with -inf padding: exact
-            src, dst = cat.slice(i * h, (i + 1) * h), cat.slice((i + 1) * h, (i + 2) * h)
-            plan.add(f"{name}.mp{5 + 4 * i}", lambda s, a=src, b=dst: L.E.maxpool5(a, b, s), "maxpool", 0.0, 4.0 * x.n * x.h * x.w * h,
-                     outs=[dict(view=dst, label=L.ref(self, f".mp{5 + 4 * i}"))])
+        sl = [cat.slice(i * h, (i + 1) * h) for i in range(4)]
+        if 3 * x.h * x.w * 32 <= 200 * 1024 and h % 16 == 0:
+            # one pass: the map is read once, the 5 / 9 / 13 pools (a 5x5 cascade in shared memory) go to their concat slices
+            plan.add(f"{name}.mp", lambda s: L.E.spp_pools(sl[0], sl[1], sl[2], sl[3], s), "maxpool", 0.0, 2.0 * 4 * x.n * x.h * x.w * h,
+                     outs=[dict(view=sl[i + 1], label=L.ref(self, f".mp{5 + 4 * i}")) for i in range(3)])
+        else:
+            for i in range(3):  # mp9 = mp5(mp5), mp13 = mp5(mp5(mp5)) with -inf padding: exact
+                plan.add(f"{name}.mp{5 + 4 * i}", lambda s, a=sl[i], b=sl[i + 1]: L.E.maxpool5(a, b, s), "maxpool", 0.0, 4.0 * x.n * x.h * x.w * h,
+                         outs=[dict(view=sl[i + 1], label=L.ref(self, f".mp{5 + 4 * i}"))])
         return self.cv2.lower(plan, cat, out, name=name + ".cv2")
 
     def forward(self, x):

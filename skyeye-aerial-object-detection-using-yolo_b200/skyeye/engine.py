@@ -181,6 +181,10 @@ def maxpool5(x: View, y: View, stream=None) -> None:
     N.check(N.lib().skb_maxpool5_bf16(x.ref, y.ref, _stream_ptr() if stream is None else stream), "skb_maxpool5_bf16")
 
 
+def spp_pools(x: View, y5: View, y9: View, y13: View, stream=None) -> None:
+    N.check(N.lib().skb_spp_pools_bf16(x.ref, y5.ref, y9.ref, y13.ref, _stream_ptr() if stream is None else stream), "skb_spp_pools_bf16")
+
+
 def cbam(x: View, w0: torch.Tensor, w1: torch.Tensor, w7: torch.Tensor, y: View, ws: torch.Tensor, stream=None) -> None:
     N.check(N.lib().skb_cbam_bf16(x.ref, w0.data_ptr(), w1.data_ptr(), w0.shape[0], w7.data_ptr(), y.ref, ws.data_ptr(),
                                   ws.numel(), _stream_ptr() if stream is None else stream), "skb_cbam_bf16")

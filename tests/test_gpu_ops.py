@@ -76,6 +76,23 @@ def test_maxpool5_cascade_equals_spp_pools_bit_exact(shape):
         assert torch.equal(got, ref), k
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 20, 20), (1, 256, 7, 9), (2, 32, 40, 40), (1, 512, 40, 40), (2, 16, 1, 3)])
+def test_fused_spp_pools_bit_exact(shape):
+    """skb_spp_pools_bf16: the 5 / 9 / 13 pools of blocks.py:143-149 in one pass, written to the concat slices behind the input."""
+    from skyeye import engine as E
+    x = bf16r(randn(("spp", shape), shape))
+    n, c, h, w = shape
+    cat = torch.zeros((n, h, w, 4 * c), dtype=torch.bfloat16, device="cuda")
+    cat[..., :c] = x.permute(0, 2, 3, 1).to(torch.bfloat16).cuda()
+    E.spp_pools(*(E.View(cat, i * c, c) for i in range(4)))
+    torch.cuda.synchronize()
+    assert torch.equal(cat[..., :c].permute(0, 3, 1, 2).float().cpu(), x)   # the input slice is untouched
+    for i, k in enumerate((5, 9, 13)):
+        ref = F.max_pool2d(x, k, 1, k // 2)
+        got = cat[..., (i + 1) * c:(i + 2) * c].permute(0, 3, 1, 2).float().cpu()
+        assert torch.equal(got, ref), k
+
+
 @pytest.mark.parametrize("shape", [(2, 256, 20, 20), (1, 512, 40, 24), (3, 64, 9, 11)])
 def test_cbam_matches_oracle(shape):
     from skyeye import engine as E
