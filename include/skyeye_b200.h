@@ -116,7 +116,7 @@ int skb_letterbox_u8(const uint8_t* src, int32_t h0, int32_t w0, int32_t src_pit
 /* nn.MaxPool2d(5, stride 1, pad 2) (blocks.py:143-144); SPP's 9 and 13 pools are cascades of it. */
 int skb_maxpool5_bf16(const skb_view* x, const skb_view* y, void* stream);
 /* SPPBlock's three pools (kernel 5, 9, 13; blocks.py:143-149) of the same map in one pass: x is read once, y5 / y9 / y13 are the
- * concat slices behind it (same shape as x, a common pixel pitch).  Maps up to 200 KB / 96 B pixels (46 x 46); larger ones
+ * concat slices behind it (same shape as x, a common pixel pitch).  Maps up to 110 KB / 64 B pixels (41 x 41); larger ones
  * return SKB_ERR_UNSUPPORTED (three skb_maxpool5_bf16 calls do the same). */
 int skb_spp_pools_bf16(const skb_view* x, const skb_view* y5, const skb_view* y9, const skb_view* y13, void* stream);
 /* CombinedAttention = ChannelAttention + SpatialAttention (attention.py:37-60, 80-98, 118-130).

@@ -222,22 +222,23 @@ __global__ void maxpool5_kernel(const __nv_bfloat16* __restrict__ x, long xpitch
 
 // SPP's three pools in ONE pass (blocks.py:143-149): a CTA owns the whole H x W map of 16 channels of one image (32 bytes per
 // pixel = one DRAM sector), reads it once into shared memory and runs the 5x5 cascade there (5, 9 = 5o5, 13 = 5o5o5: exact for
-// max with -inf padding), writing each stage's result to its concat slice.  The three chained launches above read and wrote
-// the map three times (1.6 TB/s); this reads it once and writes three slices.  Separable: row maxima into a temporary, column
-// maxima back.  Shared memory: 3 x H*W*32 B (154 KB at 40 x 40); larger maps keep the cascade of launches.
-__global__ void __launch_bounds__(256)
+// max with -inf padding), writing each stage's result to its concat slice.  Three chained launches read and wrote the map three
+// times; this reads it once and writes three slices.  Separable: row maxima A -> T, column maxima T -> A (A is dead once its row
+// maxima exist, so two buffers do: 2 x H*W*32 B = 102 KB at 40 x 40, two CTAs of 512 threads per SM); larger maps keep the
+// cascade of launches.  A thread owns one 16-byte vector column-slot and walks it with a sliding window (no per-item division).
+constexpr int SPP_THREADS = 512;
+__global__ void __launch_bounds__(SPP_THREADS, 2)
 spp_fused_kernel(const __nv_bfloat16* __restrict__ x, long xpitch, __nv_bfloat16* __restrict__ y5, __nv_bfloat16* __restrict__ y9,
                  __nv_bfloat16* __restrict__ y13, long ypitch, int H, int W, int groups) {
     extern __shared__ __align__(16) uint4 spp_smem[];
     const int items = H * W * 2;  // 16-byte vectors: [y][x][2]
-    uint4* A = spp_smem;          // current stage input
+    uint4* A = spp_smem;          // stage input / output
     uint4* T = A + items;         // row maxima
-    uint4* B = T + items;         // stage output
     const int n = blockIdx.x / groups, cg = blockIdx.x - n * groups;
     const long img = (long)n * H * W;
-    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    for (int i = threadIdx.x; i < items; i += SPP_THREADS) {
         const int pix = i >> 1, v = i & 1;
-        A[i] = *reinterpret_cast<const uint4*>(x + (img + pix) * xpitch + cg * 16 + v * 8);
+        A[i] = __ldg(reinterpret_cast<const uint4*>(x + (img + pix) * xpitch + cg * 16 + v * 8));
     }
     __syncthreads();
     auto vmax = [](uint4 a, const uint4& b) {
@@ -248,26 +249,31 @@ spp_fused_kernel(const __nv_bfloat16* __restrict__ x, long xpitch, __nv_bfloat16
         return a;
     };
     __nv_bfloat16* outs[3] = {y5, y9, y13};
+    const int W2 = W * 2;
 #pragma unroll 1
     for (int stage = 0; stage < 3; ++stage) {
-        for (int i = threadIdx.x; i < items; i += blockDim.x) {  // horizontal 5-max
-            const int pix = i >> 1, v = i & 1, py = pix / W, px = pix - py * W;
-            const int xa = max(px - 2, 0), xb = min(px + 2, W - 1);
-            uint4 m = A[(py * W + xa) * 2 + v];
-            for (int xx = xa + 1; xx <= xb; ++xx) m = vmax(m, A[(py * W + xx) * 2 + v]);
+        for (int i = threadIdx.x; i < items; i += SPP_THREADS) {  // horizontal 5-max (clamped window = -inf padding)
+            const int pix = i >> 1, px = pix % W;
+            uint4 m = A[i];
+            if (px >= 1) m = vmax(m, A[i - 2]);
+            if (px >= 2) m = vmax(m, A[i - 4]);
+            if (px + 1 < W) m = vmax(m, A[i + 2]);
+            if (px + 2 < W) m = vmax(m, A[i + 4]);
             T[i] = m;
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < items; i += blockDim.x) {  // vertical 5-max, store
-            const int pix = i >> 1, v = i & 1, py = pix / W, px = pix - py * W;
-            const int ya = max(py - 2, 0), yb = min(py + 2, H - 1);
-            uint4 m = T[(ya * W + px) * 2 + v];
-            for (int yy = ya + 1; yy <= yb; ++yy) m = vmax(m, T[(yy * W + px) * 2 + v]);
-            B[i] = m;
-            *reinterpret_cast<uint4*>(outs[stage] + (img + pix) * ypitch + cg * 16 + v * 8) = m;
+        __nv_bfloat16* out = outs[stage] + cg * 16;
+        for (int i = threadIdx.x; i < items; i += SPP_THREADS) {  // vertical 5-max, store
+            const int pix = i >> 1, v = i & 1, py = pix / W;
+            uint4 m = T[i];
+            if (py >= 1) m = vmax(m, T[i - W2]);
+            if (py >= 2) m = vmax(m, T[i - 2 * W2]);
+            if (py + 1 < H) m = vmax(m, T[i + W2]);
+            if (py + 2 < H) m = vmax(m, T[i + 2 * W2]);
+            A[i] = m;  // the stage's output is the next stage's input
+            *reinterpret_cast<uint4*>(out + (img + pix) * ypitch + v * 8) = m;
         }
         __syncthreads();
-        uint4* t = A; A = B; B = t;  // the stage's output is the next stage's input
     }
 }
 
@@ -854,12 +860,12 @@ extern "C" int skb_spp_pools_bf16(const skb_view* x, const skb_view* y5, const s
         SKB_REQUIRE(ys[i]->n == x->n && ys[i]->h == x->h && ys[i]->w == x->w && ys[i]->c == x->c && ys[i]->pitch == y5->pitch, SKB_ERR_ARG,
                     "spp_pools: output %d does not match the input map", i);
     SKB_REQUIRE(x->c % 16 == 0, SKB_ERR_UNSUPPORTED, "spp_pools: C=%d must be a multiple of 16", x->c);
-    const size_t smem = (size_t)3 * x->h * x->w * 32;
-    SKB_REQUIRE(smem <= 200 * 1024, SKB_ERR_UNSUPPORTED, "spp_pools: %dx%d map needs %zu bytes of shared memory (use skb_maxpool5_bf16 x 3)", x->h, x->w, smem);
+    const size_t smem = (size_t)2 * x->h * x->w * 32;
+    SKB_REQUIRE(smem <= 110 * 1024, SKB_ERR_UNSUPPORTED, "spp_pools: %dx%d map needs %zu bytes of shared memory (use skb_maxpool5_bf16 x 3)", x->h, x->w, smem);
     static PerDeviceOnce once;
-    if (once.first()) SKB_CUDA(cudaFuncSetAttribute(spp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (once.first()) SKB_CUDA(cudaFuncSetAttribute(spp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     const int groups = x->c / 16;
-    spp_fused_kernel<<<x->n * groups, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x->ptr, x->pitch, (__nv_bfloat16*)y5->ptr,
+    spp_fused_kernel<<<x->n * groups, SPP_THREADS, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x->ptr, x->pitch, (__nv_bfloat16*)y5->ptr,
                                                                          (__nv_bfloat16*)y9->ptr, (__nv_bfloat16*)y13->ptr, y5->pitch, x->h, x->w, groups);
     SKB_LAUNCH_CHECK();
     return SKB_OK;

@@ -104,7 +104,7 @@ class SPPBlock(nn.Module):
         cat = plan.buf(x.n, x.h, x.w, 4 * h)
         self.cv1.lower(plan, x, cat.slice(0, h), name=name + ".cv1")
         sl = [cat.slice(i * h, (i + 1) * h) for i in range(4)]
-        if 3 * x.h * x.w * 32 <= 200 * 1024 and h % 16 == 0:
+        if 2 * x.h * x.w * 32 <= 110 * 1024 and h % 16 == 0:
             # one pass: the map is read once, the 5 / 9 / 13 pools (a 5x5 cascade in shared memory) go to their concat slices
             plan.add(f"{name}.mp", lambda s: L.E.spp_pools(sl[0], sl[1], sl[2], sl[3], s), "maxpool", 0.0, 2.0 * 4 * x.n * x.h * x.w * h,
                      outs=[dict(view=sl[i + 1], label=L.ref(self, f".mp{5 + 4 * i}")) for i in range(3)])
