@@ -609,6 +609,273 @@ window_attn_kernel(const __nv_bfloat16* __restrict__ qkv, long qpitch, const flo
 
 }  // namespace skb
 
+// =============================================================================================
+// Tensor-core form of the same core for the shape the detector uses (64-token windows, head_dim 64, no mask): the CUDA-core
+// kernel above runs ~14 TFLOP/s (1.95 ms for the P3 level of skyeye_lw at B16) where reading qkv and writing o once costs
+// 0.13 ms.  One persistent CTA per SM owns ONE head (its relative-position bias, pre-multiplied by log2 e, stays in shared
+// memory) and walks pairs of windows: the Q, K and V head slices of two windows are six 8 KB TMA boxes ({64 ch, 8 x, 8 y}
+// out of the unpartitioned map, or 64 consecutive tokens of the class layout) stacked into three 128-row operand tiles.
+//   S = Q K^T   one M128 x N128 x K64 tcgen05.mma (SS form); only the two diagonal 64 x 64 blocks are meaningful
+//   P           thread <-> query row: tcgen05.ld of its window's 64 scores, s * scale + bias, exact softmax (the whole row is
+//               here: no online rescaling), bf16 P written over S with tcgen05.st -- zeros in the other window's key columns
+//   O = P V     one M128 x N64 x K128 tcgen05.mma (A = P from TMEM, B = both windows' V, MN-major)
+// Half of the tensor work multiplies zeros: 576 MMA cycles per pair against ~2400 cycles of HBM time for its 64 KB, so the
+// kernel stays HBM-bound.  Two softmax warpgroups alternate pairs (each owns one S/P and one O buffer in TMEM: 384 columns),
+// a three-stage TMA ring (144 KB) keeps ~100 KB per SM in flight.
+// =============================================================================================
+namespace skb {
+
+constexpr int WA_STAGES = 3;
+constexpr int WA_TILE = 64 * 128;            // one window's Q, K or V slice of one head: 64 tokens x 128 B
+constexpr int WA_STAGE = 6 * WA_TILE;        // Q[2 windows] K[2] V[2]
+constexpr int WA_THREADS = 320;              // warp 0 TMA, warp 1 MMA, warps 2..5 / 6..9 softmax + epilogue groups
+constexpr int WA_SMEM = WA_STAGES * WA_STAGE + 64 * 64 * 4 + 1024 + 256;
+
+struct WinAttnParams {
+    int n_windows, n_pairs, heads, C;
+    int mode2d, ws, Wimg, Himg, wins_x, wins_per_img;
+    float scale_log2;
+    const float* bias;   // [heads][64][64]
+    __nv_bfloat16* out;
+    long opitch;
+};
+
+__global__ void __launch_bounds__(WA_THREADS, 1)
+window_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const WinAttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t sBias = base + WA_STAGES * WA_STAGE;   // fp32 [16 key quads][64 tokens][4]: conflict-free 16-byte reads
+    const uint32_t bar0 = sBias + 64 * 64 * 4;
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (WA_STAGES + s); };
+    auto s_full = [&](int b) { return bar0 + 8u * (2 * WA_STAGES + b); };
+    auto p_full = [&](int b) { return bar0 + 8u * (2 * WA_STAGES + 2 + b); };
+    auto o_full = [&](int b) { return bar0 + 8u * (2 * WA_STAGES + 4 + b); };
+    const uint32_t slot = bar0 + 8u * (2 * WA_STAGES + 6);
+    volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - raw));
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int head = blockIdx.x % p.heads, slot_id = blockIdx.x / p.heads, n_slots = gridDim.x / p.heads;
+    const int n_my = slot_id < p.n_pairs ? (p.n_pairs - slot_id + n_slots - 1) / n_slots : 0;  // pairs slot_id, slot_id + n_slots, ...
+
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tm);
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < WA_STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+            for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(p_full(b), 4); mbar_init(o_full(b), 1); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(slot, 512);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *slot_ptr, 0);
+    // TMEM columns: S/P buffer b at b * 128 (128 fp32 score columns; P = 64 columns of packed bf16 over them), O buffer b at 256 + b * 64
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        const bool lead = elect_one();
+        for (int i = 0; i < n_my; ++i) {
+            const int s = i % WA_STAGES;
+            mbar_wait(empty(s), ((uint32_t)(i / WA_STAGES) & 1u) ^ 1u);
+            if (lead) {
+                mbar_expect_tx(full(s), WA_STAGE);
+                const int pair = slot_id + i * n_slots;
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    const int win = min(2 * pair + w, p.n_windows - 1);  // an odd tail reloads the last window (its rows are not stored)
+                    const uint32_t dst = base + s * WA_STAGE + w * WA_TILE;
+                    if (p.mode2d) {
+                        const int n = win / p.wins_per_img, r = win - n * p.wins_per_img;
+                        const int wy = r / p.wins_x, wx = r - wy * p.wins_x;
+#pragma unroll
+                        for (int m = 0; m < 3; ++m)
+                            tma_load_4d(dst + m * 2 * WA_TILE, &tm, full(s), m * p.C + head * 64, wx * 8, wy * 8, n);
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < 3; ++m) tma_load_3d(dst + m * 2 * WA_TILE, &tm, full(s), m * p.C + head * 64, 0, win);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);  // A = Q (smem, K-major), B = K (smem, K-major)
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);   // A = P (TMEM), B = V (smem, MN-major)
+        auto issue_pv = [&](int k) {
+            const int b = k & 1, s = k % WA_STAGES;
+            mbar_wait(p_full(b), (uint32_t)(k >> 1) & 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t vd = umma_desc(base + s * WA_STAGE + 4 * WA_TILE, 16, 1024, UMMA_SW128);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)  // 16 keys per MMA: 8 TMEM columns of A, 2048 B of V
+                    umma_bf16_ts(tmem_base + 256 + b * 64, tmem_base + b * 128 + kk * 8, vd + (uint64_t)(kk * 128), idesc_pv, kk > 0);
+                umma_commit(empty(s));
+                umma_commit(o_full(b));
+            }
+            __syncwarp();
+        };
+        for (int i = 0; i < n_my; ++i) {
+            const int s = i % WA_STAGES, b = i & 1;
+            mbar_wait(full(s), (uint32_t)(i / WA_STAGES) & 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t qd = umma_desc(base + s * WA_STAGE, 16, 1024, UMMA_SW128);
+                const uint64_t kd = umma_desc(base + s * WA_STAGE + 2 * WA_TILE, 16, 1024, UMMA_SW128);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tmem_base + b * 128, qd + (uint64_t)(kk * 2), kd + (uint64_t)(kk * 2), idesc_qk, kk > 0);
+                umma_commit(s_full(b));
+            }
+            __syncwarp();
+            if (i > 0) issue_pv(i - 1);  // in-order MMA execution: QK(i + 1) overwrites S/P buffer b^1 only after PV(i - 1) has read it
+        }
+        if (n_my > 0) issue_pv(n_my - 1);
+    } else {
+        // ===================== softmax + epilogue group grp: pairs i = grp, grp + 2, ... (S/P and O buffer grp) =====================
+        const int grp = (warp - 2) >> 2;
+        const int q = warp & 3;                       // TMEM lane quadrant of this warp
+        const int row = q * 32 + lane, w = row >> 6, t = row & 63;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const uint32_t tS = tmem_base + grp * 128 + lane_addr, tO = tmem_base + 256 + grp * 64 + lane_addr;
+        {   // bias[head][t][j] * log2(e) -> shared [j / 4][t][j % 4]
+            const float* bsrc = p.bias + (long)head * 64 * 64;
+            for (int i = threadIdx.x - 64; i < 64 * 64; i += 256) {
+                const int tt = i >> 6, j = i & 63;
+                sts32f(sBias + (uint32_t)(((j >> 2) * 64 + tt) * 4 + (j & 3)) * 4u, bsrc[i] * 1.4426950408889634f);
+            }
+            named_bar_sync(1, 256);
+        }
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+        for (int i = grp; i < n_my; i += 2) {
+            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            mbar_wait(s_full(grp), ph);
+            tc_fence_after();
+            uint32_t sv[64];
+            {
+                uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
+                uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
+                tmem_ld32(tS + w * 64, lo);
+                tmem_ld32(tS + w * 64 + 32, hi);
+            }
+            tmem_ld_wait();
+            float x[64];
+            float m8[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int j4 = 0; j4 < 16; ++j4) {
+                const float4 bv = lds128f(sBias + (uint32_t)(j4 * 64 + t) * 16u);
+                const float2 a = ffma2(make_float2(__uint_as_float(sv[4 * j4]), __uint_as_float(sv[4 * j4 + 1])), sc2, make_float2(bv.x, bv.y));
+                const float2 c = ffma2(make_float2(__uint_as_float(sv[4 * j4 + 2]), __uint_as_float(sv[4 * j4 + 3])), sc2, make_float2(bv.z, bv.w));
+                x[4 * j4] = a.x; x[4 * j4 + 1] = a.y; x[4 * j4 + 2] = c.x; x[4 * j4 + 3] = c.y;
+                m8[0] = fmaxf(m8[0], a.x); m8[1] = fmaxf(m8[1], a.y); m8[2] = fmaxf(m8[2], c.x); m8[3] = fmaxf(m8[3], c.y);
+            }
+            const float mx = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+            uint32_t pk[32];
+            float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float e0 = ex2_approx(x[2 * j] - mx), e1 = ex2_approx(x[2 * j + 1] - mx);
+                l4[(2 * j) & 3] += e0;
+                l4[(2 * j + 1) & 3] += e1;
+                pk[j] = pack_bf16x2(e0, e1);
+            }
+            const float inv = 1.0f / ((l4[0] + l4[1]) + (l4[2] + l4[3]));
+            {   // P: this window's 64 keys are columns [w * 32, w * 32 + 32) of the packed row, the other window's are zeros
+                uint32_t z[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) z[j] = 0u;
+                tmem_st32(tS + w * 32, pk);
+                tmem_st32(tS + (w ^ 1) * 32, z);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full(grp));
+            // ---- epilogue: O / l -> bf16, 128 contiguous bytes per token ----
+            const int pair = slot_id + i * n_slots, win = 2 * pair + w;
+            long tok;
+            if (p.mode2d) {
+                const int n = win / p.wins_per_img, r = win - n * p.wins_per_img;
+                const int wy = r / p.wins_x, wx = r - wy * p.wins_x;
+                tok = ((long)n * p.Himg + wy * 8 + (t >> 3)) * p.Wimg + wx * 8 + (t & 7);
+            } else {
+                tok = (long)win * 64 + t;
+            }
+            __nv_bfloat16* dst = p.out + tok * p.opitch + head * 64;
+            mbar_wait(o_full(grp), ph);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t o[32];
+                tmem_ld32(tO + h * 32, o);
+                tmem_ld_wait();
+                if (win < p.n_windows) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 u;
+                        u.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+                        u.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+                        u.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+                        u.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+                        *reinterpret_cast<uint4*>(dst + h * 32 + g * 8) = u;
+                    }
+                }
+            }
+            tc_fence_before();  // the O loads are complete before the next p_full arrive lets PV(i + 2) overwrite the buffer
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace skb
+
+// Launches the tensor-core window kernel when the shape is the detector's (64 tokens, head_dim 64, no mask); returns 1 if it did.
+static int window_attn_tc_try(const skb_view* qkv, const float* bias, const float* mask, const skb_view* o, int heads, int window,
+                              float scale, cudaStream_t st, int* launched) {
+    *launched = 0;
+    const int C = o->c;
+    static int use_tc = -1;  // tuning knob (not part of the ABI): SKB_WATT_TC=0 keeps the CUDA-core kernel
+    if (use_tc < 0) { const char* e = getenv("SKB_WATT_TC"); use_tc = e ? atoi(e) : 1; }
+    const int n_tok = window > 0 ? window * window : qkv->w;
+    if (!use_tc || mask || C != heads * 64 || n_tok != 64 || heads > num_sms()) return SKB_OK;
+    WinAttnParams p;
+    CUtensorMap tm;
+    int rc;
+    if (window > 0) {
+        p.mode2d = 1; p.ws = window; p.Wimg = qkv->w; p.Himg = qkv->h; p.wins_x = qkv->w / window; p.wins_per_img = p.wins_x * (qkv->h / window);
+        p.n_windows = qkv->n * p.wins_per_img;
+        uint64_t dims[4] = {(uint64_t)qkv->c, (uint64_t)qkv->w, (uint64_t)qkv->h, (uint64_t)qkv->n};
+        uint64_t str[3] = {(uint64_t)qkv->pitch * 2, (uint64_t)qkv->pitch * 2 * qkv->w, (uint64_t)qkv->pitch * 2 * qkv->w * qkv->h};
+        uint32_t box[4] = {64, 8, 8, 1};
+        rc = encode_tensor_map(&tm, qkv->ptr, 2, 4, dims, str, box, 128);
+    } else {
+        p.mode2d = 0; p.ws = 0; p.Wimg = 0; p.Himg = 0; p.wins_x = 1; p.wins_per_img = 1;
+        p.n_windows = qkv->n;
+        uint64_t dims[3] = {(uint64_t)qkv->c, 64, (uint64_t)qkv->n};
+        uint64_t str[2] = {(uint64_t)qkv->pitch * 2, (uint64_t)qkv->pitch * 2 * 64};
+        uint32_t box[3] = {64, 64, 1};
+        rc = encode_tensor_map(&tm, qkv->ptr, 2, 3, dims, str, box, 128);
+    }
+    if (rc != SKB_OK) return rc;
+    p.n_pairs = (p.n_windows + 1) / 2; p.heads = heads; p.C = C;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.bias = bias; p.out = (__nv_bfloat16*)o->ptr; p.opitch = o->pitch;
+    static PerDeviceOnce once;
+    if (once.first()) SKB_CUDA(cudaFuncSetAttribute(window_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
+    int slots = num_sms() / heads;
+    if (slots > p.n_pairs) slots = p.n_pairs;
+    window_attn_tc_kernel<<<heads * slots, WA_THREADS, WA_SMEM, st>>>(tm, p);
+    SKB_LAUNCH_CHECK();
+    *launched = 1;
+    return SKB_OK;
+}
+
 extern "C" int skb_window_attn_bf16(const skb_view* qkv, const float* bias, const float* mask, int32_t n_mask, const skb_view* o,
                                     int32_t heads, float scale, void* stream) {
     int rc = check_device();
@@ -626,6 +893,11 @@ extern "C" int skb_window_attn_bf16(const skb_view* qkv, const float* bias, cons
     const int N = qkv->w;
     dim3 grid(qkv->n, heads);
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        int launched = 0;
+        rc = window_attn_tc_try(qkv, bias, mask, o, heads, 0, scale, st, &launched);
+        if (rc != SKB_OK || launched) return rc;
+    }
     const __nv_bfloat16* qp = (const __nv_bfloat16*)qkv->ptr;
     __nv_bfloat16* op = (__nv_bfloat16*)o->ptr;
     if (hd == 64) window_attn_kernel<64><<<grid, 64, 0, st>>>(qp, qkv->pitch, bias, mask, n_mask, op, o->pitch, N, C, scale, 0, 0, 1, 1);
@@ -653,6 +925,11 @@ extern "C" int skb_window_attn2d_bf16(const skb_view* qkv, const float* bias, co
     const int N = window * window, wins_x = qkv->w / window, wpi = wins_x * (qkv->h / window);
     dim3 grid(qkv->n * wpi, heads);
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        int launched = 0;
+        rc = window_attn_tc_try(qkv, bias, mask, o, heads, window, scale, st, &launched);
+        if (rc != SKB_OK || launched) return rc;
+    }
     const __nv_bfloat16* qp = (const __nv_bfloat16*)qkv->ptr;
     __nv_bfloat16* op = (__nv_bfloat16*)o->ptr;
     if (hd == 64) window_attn_kernel<64><<<grid, 64, 0, st>>>(qp, qkv->pitch, bias, mask, n_mask, op, o->pitch, N, C, scale, window, qkv->w, wins_x, wpi);

@@ -259,6 +259,26 @@ def test_windowed_self_attention_matches_oracle(name):
     assert rel_err(got, ref) < TOL
 
 
+@pytest.mark.parametrize("B,H,W,C,heads", [(2, 80, 80, 512, 8), (1, 40, 24, 256, 4), (3, 8, 8, 64, 1), (1, 16, 8, 1024, 16)])
+def test_window_attn2d_tensor_core_path_matches_fp32_reference(B, H, W, C, heads):
+    """skb_window_attn2d_bf16 on the shape class the detector uses (8 x 8 windows, head_dim 64, no mask: the persistent tcgen05
+    kernel, pairs of windows per tile, several tiles per CTA, odd window counts) vs softmax(q k^T * scale + bias) v
+    (attention.py:372-395) in fp32 on the same bf16 qkv, windows partitioned / reversed explicitly."""
+    from skyeye import engine as E
+    from skyeye.core.models.attention import window_partition, window_reverse
+    qkv = bf16r(randn(("wa2d", B, H, W, C), (B, H, W, 3 * C)))
+    bias = randn(("wa2d-bias", heads), (heads, 64, 64))
+    scale = 64 ** -0.5
+    o = E.new_buffer(B, H, W, C)
+    o.t.fill_(7.0)
+    E.window_attn2d(E.View(qkv.to(torch.bfloat16).cuda()), bias.cuda(), None, o, heads, 8, scale)
+    torch.cuda.synchronize()
+    wins = window_partition(qkv, 8).view(-1, 64, 3, heads, 64).permute(2, 0, 3, 1, 4)      # [3, nW, heads, 64, 64]
+    att = torch.softmax(wins[0] @ wins[1].transpose(-2, -1) * scale + bias.unsqueeze(0), dim=-1) @ wins[2]
+    ref = window_reverse(att.transpose(1, 2).reshape(-1, 64, C), 8, H, W)
+    assert rel_err(o.torch().float().cpu(), ref) < TOL   # NHWC both
+
+
 @pytest.mark.parametrize("hw,new", [((100, 200), 128), ((720, 1280), 640), ((333, 517), 256), ((64, 96), 96), ((96, 128), 128),
                                     ((50, 70), 160)])
 def test_letterbox_gpu_matches_cv2_pipeline(hw, new):
