@@ -487,9 +487,43 @@ def run_b200(args):
         att_g = table["attention"]["ms_per_step"]
         windowed = {"variant": "skyeye_lw (head: windowed, window_size 8)", "images_per_s": B / (ms_w / 1e3), "ms_per_step": ms_w,
                     "attention_ms_per_step": att_w, "global_attention_ms_per_step": att_g,
-                    "note": "window attention core = skb_window_attn2d_bf16 (CUDA-core kernel, one CTA per window and head); "
-                            "detections differ from skyeye_l by construction (a different head)"}
+                    "note": "window attention core = skb_window_attn2d_bf16 (persistent tcgen05 kernel: pairs of 64-token windows per "
+                            "M128 tile, HBM-bound); detections differ from skyeye_l by construction (a different head)"}
         del mw, pw
+
+    # Informational: SURVEY.md §8(d) config 2 -- skyeye_s (plain CSP / PAN detector, conv heads) at 640^2, batch 32, same protocol
+    # (inputs resident, CUDA-graph replay, forward + decode + NMS); plain seeded init (the variant is well conditioned as it is).
+    config2 = None
+    if world == 1 and not args.no_variants and args.variant == VARIANT and S == H:
+        from oracle import model as om2
+        cfg_s = om2.get_cfg("skyeye_s")
+        ms_model = construct_model("skyeye_s.yaml")
+        ms_model.load_state_dict(om2.make_state_dict(cfg_s, 0), strict=True)
+        ms_model = ms_model.to(dev).eval()
+        ms_model.reuse_output_buffers = True
+        xs = torch.from_numpy(synthetic_images(32, 640, 99)).to(dev)
+        o2 = torch.zeros((32, MAX_DET, 7), dtype=torch.float32, device=dev)
+        c2 = torch.zeros(32, dtype=torch.int32, device=dev)
+
+        def step_s():
+            ds, _ = ms_model(xs)
+            batched_nms_padded(ds, CONF, IOU, max_detections=MAX_DET, out=o2, out_count=c2)
+
+        for _ in range(5):
+            step_s()
+        ssteps = 30
+        ms_s = timed(step_s, ssteps) / ssteps
+        ps = ms_model.plan_for(xs)
+        ms_model._img[0] = xs
+        rows_s = ps.run_timed()
+        fl_s = sum(m["flops"] for m in ps.meta)
+        by_s = sum(m["bytes"] for m in ps.meta)
+        config2 = {"variant": "skyeye_s 640x640 batch 32 (SURVEY §8d config 2)", "images_per_s": 32 / (ms_s / 1e3), "ms_per_step": ms_s,
+                   "kernel_ms_per_step": sum(ms for nm, ms in rows_s), "launches": ps.launches + NMS_LAUNCHES,
+                   "algorithmic_tflops": fl_s / 1e12, "algorithmic_gbytes": by_s / 1e9,
+                   "tflops": fl_s / (ms_s * 1e9), "gbs": by_s / (ms_s * 1e6),
+                   "note": "HBM-bound network (most layers below the 206 flop/B ridge): gbs counts each launch's unfused bf16 input + weights + output"}
+        del ms_model, ps, xs
 
     launches_per_step = plan.launches + NMS_LAUNCHES
     from skyeye.engine import View
@@ -544,6 +578,7 @@ def run_b200(args):
             "parity": parity,
             "tiled4k": tiled,
             "windowed_head": windowed,
+            "config2_skyeye_s": config2,
             "latency_b1": latency,
             "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in table.items()},
         }
