@@ -56,22 +56,31 @@ struct alignas(16) SortScratch {
     unsigned long long result;
 };
 
-// f(key) for every key of g[0, n): eight independent coalesced loads per thread are in flight before the first is used (the
-// one-load-per-iteration form was latency-bound: ~700 cycles per key and thread, 0.4 ms for a 100 000-key image).
+// f(key) for every key of g[0, n): eight independent coalesced 16-byte loads (two keys each) per thread are in flight before the
+// first is used (the one-load-per-iteration form was latency-bound: ~700 cycles per key and thread, 0.4 ms for a 100 000-key
+// image).  A segment that starts on an odd key is peeled by one key; an odd tail key is read on its own.
 template <typename F>
 __device__ __forceinline__ void cta_for_each_key(const unsigned long long* g, int n, F f) {
     constexpr int U = 8;
-    for (int base = 0; base < n; base += NMS_THREADS * U) {
-        unsigned long long kbuf[U];
+    if (n > 0 && (reinterpret_cast<uintptr_t>(g) & 8)) {  // segment start on an odd key: peel it
+        if (threadIdx.x == 0) f(g[0]);
+        ++g;
+        --n;
+    }
+    const int n2 = n >> 1;
+    const ulonglong2* g2 = reinterpret_cast<const ulonglong2*>(g);
+    for (int base = 0; base < n2; base += NMS_THREADS * U) {
+        ulonglong2 kbuf[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int i = base + u * NMS_THREADS + (int)threadIdx.x;
-            kbuf[u] = i < n ? g[i] : 0ULL;
+            kbuf[u] = i < n2 ? g2[i] : make_ulonglong2(0ULL, 0ULL);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (base + u * NMS_THREADS + (int)threadIdx.x < n) f(kbuf[u]);
+            if (base + u * NMS_THREADS + (int)threadIdx.x < n2) { f(kbuf[u].x); f(kbuf[u].y); }
     }
+    if ((n & 1) && threadIdx.x == 0) f(g[n - 1]);
 }
 
 // The k-th smallest (k >= 1) of the keys in g[0, n) that are > lo (all keys if !have_lo).  Only the low `total_bits` bits
@@ -178,9 +187,19 @@ __device__ unsigned long long cta_sampled_cut(const unsigned long long* g, int n
     const int stride = max(1, n >> 12);  // <= 8192 samples
     for (int i = tid; i < SEL_BINS; i += NMS_THREADS) S.hist[i] = 0u;
     __syncthreads();
-    for (int j = tid; (long)j * stride < n; j += NMS_THREADS) {
-        const unsigned long long key = g[(long)j * stride];
-        if (!have_lo || key > lo) atomicAdd(&S.hist[(unsigned int)((key & kmask) >> shift) & ((1u << nb) - 1u)], 1u);
+    for (int j0 = tid; (long)j0 * stride < n; j0 += 4 * NMS_THREADS) {  // four sample loads in flight per thread
+        unsigned long long kb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long idx = (long)(j0 + u * NMS_THREADS) * stride;
+            kb[u] = idx < n ? g[idx] : 0ULL;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned long long key = kb[u];
+            if ((long)(j0 + u * NMS_THREADS) * stride < n && (!have_lo || key > lo))
+                atomicAdd(&S.hist[(unsigned int)((key & kmask) >> shift) & ((1u << nb) - 1u)], 1u);
+        }
     }
     __syncthreads();
     const unsigned int target = (unsigned int)max(1, (want - want / 4) / stride);  // aim at 3/4 of the capacity
@@ -550,7 +569,7 @@ nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict_
     __shared__ int surv[NMS_THREADS];   // chunk-local ids of phase-A survivors, in order
     __shared__ int warp_cnt[NMS_THREADS / 32];
     __shared__ int s_nsurv, s_kept;
-    __shared__ float cx1[NMS_THREADS], cy1[NMS_THREADS], cx2[NMS_THREADS], cy2[NMS_THREADS], car[NMS_THREADS];
+    __shared__ float sx1[NMS_THREADS], sy1[NMS_THREADS], sx2[NMS_THREADS], sy2[NMS_THREADS], sar[NMS_THREADS];  // survivor boxes, compacted
     __shared__ float crow[NMS_THREADS][7];
     extern __shared__ __align__(16) unsigned int smask[];  // [NMS_THREADS][NMS_THREADS / 32] pairwise suppression bits of a chunk (32 KB)
     unsigned long long* skeys = reinterpret_cast<unsigned long long*>(smask + NMS_THREADS * (NMS_THREADS / 32));  // the round's sorted keys (64 KB)
@@ -576,9 +595,12 @@ nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict_
     const int common_bits = __clz((int)(v_or ^ v_and));  // leading score bits all of this image's keys share
     const unsigned long long common = common_bits ? (unsigned long long)(v_or >> (32 - common_bits)) : 0ULL;
 
+    // A detector's image is usually done inside its first few hundred candidates: the first round orders only ~4 * max_det keys
+    // (a 1024-key bitonic sort instead of an 8192-key one), later rounds take full batches.
+    const int want0 = min(SORT_KS, max(1024, 4 * p.max_det));
     while (consumed < n_cap && s_kept < p.max_det) {
-    const int m_batch = cta_next_sorted_batch(gkeys, n_all, have_lo, lo, n_all - consumed, min(SORT_KS, n_cap - consumed), 32 + p.slot_bits,
-                                              common_bits, common, skeys, S);
+    const int m_batch = cta_next_sorted_batch(gkeys, n_all, have_lo, lo, n_all - consumed, min(consumed == 0 ? want0 : SORT_KS, n_cap - consumed),
+                                              32 + p.slot_bits, common_bits, common, skeys, S);
     const int n = min(m_batch, n_cap - consumed);  // the batch may run past the 30 000-candidate cap: the tail is not walked
     lo = skeys[n - 1];
     have_lo = true;
@@ -610,34 +632,38 @@ nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict_
         if (alive) {
             const int pos = wbase + __popc(bal & ((1u << lane) - 1u));
             surv[pos] = tid;
+            sx1[pos] = c.x1; sy1[pos] = c.y1; sx2[pos] = c.x2; sy2[pos] = c.y2; sar[pos] = c.area;
         }
         if (tid == NMS_THREADS - 1) s_nsurv = wbase + __popc(bal);
-        cx1[tid] = c.x1; cy1[tid] = c.y1; cx2[tid] = c.x2; cy2[tid] = c.y2; car[tid] = c.area;
 #pragma unroll
         for (int q = 0; q < 7; ++q) crow[tid][q] = c.row[q];
         __syncthreads();
         // phase B1: pairwise suppression masks among this chunk's survivors, in parallel.  Row s (survivor position s) has
-        // bit j of word j / 32 set iff survivor j < s overlaps s by more than the threshold (same arithmetic as everywhere:
-        // a zero intersection gives 0 or NaN, never > thr, so it short-cuts the division).
+        // bit j of word w set iff survivor 32 w + j < s overlaps s by more than the threshold (same arithmetic as everywhere:
+        // a zero intersection gives 0 or NaN, never > thr, so it short-cuts the division).  The triangle of (word, row) tasks
+        // -- word w pairs with rows 32 w .. ns - 1 -- is dealt out flat, one task = 32 column boxes (broadcast reads) against one
+        // row box, independent loads: the row-per-thread form walked up to 511 dependent shared-memory chains of ~230 cycles
+        // (117 000 cycles for a full chunk; this is ~3 000).
         {
             const int ns = s_nsurv;
-            if (tid < ns) {
-                const int t = surv[tid];
-                const float ax1 = cx1[t], ay1 = cy1[t], ax2 = cx2[t], ay2 = cy2[t], aar = car[t];
-                for (int w = 0; w <= (tid >> 5); ++w) {
-                    const int j0 = w * 32, j1 = min(j0 + 32, tid);
-                    unsigned int m = 0;
-                    if (COUNT) n_pairs += (unsigned int)(j1 - j0);
-                    for (int j = j0; j < j1; ++j) {
-                        const int u = surv[j];
-                        const float xx1 = fmaxf(cx1[u], ax1), yy1 = fmaxf(cy1[u], ay1);
-                        const float xx2 = fminf(cx2[u], ax2), yy2 = fminf(cy2[u], ay2);
-                        if (xx2 > xx1 && yy2 > yy1 &&
-                            iou_gt(cx1[u], cy1[u], cx2[u], cy2[u], car[u], ax1, ay1, ax2, ay2, aar, p.iou))
-                            m |= 1u << (j - j0);
-                    }
-                    smask[tid * (NMS_THREADS / 32) + w] = m;
+            const int nw = (ns + 31) >> 5;
+            const int n_tasks = nw * ns - 16 * nw * (nw - 1);   // sum over w of (ns - 32 w)
+            int w = 0, start = 0;                                 // tasks of word w are [start, start + ns - 32 w)
+            for (int q = tid; q < n_tasks; q += NMS_THREADS) {
+                while (q >= start + ns - 32 * w) { start += ns - 32 * w; ++w; }
+                const int s = 32 * w + (q - start);
+                const float ax1 = sx1[s], ay1 = sy1[s], ax2 = sx2[s], ay2 = sy2[s], aar = sar[s];
+                const int jn = min(32, s - 32 * w);               // columns of this word that precede row s
+                if (COUNT) n_pairs += (unsigned int)jn;
+                unsigned int m = 0;
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) {
+                    const int u = 32 * w + j;
+                    const float bx1 = sx1[u], by1 = sy1[u], bx2 = sx2[u], by2 = sy2[u];
+                    const bool ov = (fminf(bx2, ax2) > fmaxf(bx1, ax1)) & (fminf(by2, ay2) > fmaxf(by1, ay1)) & (j < jn);
+                    if (ov && iou_gt(bx1, by1, bx2, by2, sar[u], ax1, ay1, ax2, ay2, aar, p.iou)) m |= 1u << j;
                 }
+                smask[s * (NMS_THREADS / 32) + w] = m;
             }
         }
         __syncthreads();
@@ -660,17 +686,22 @@ nms_keptlist_kernel(const BatchedParams p, const unsigned long long* __restrict_
                     if (valid && (mrow[w] & kww) != 0u) dead = true;
                 }
                 const unsigned int diag = valid ? mrow[G] : 0u;  // earlier survivors of this group that overlap survivor s
+                // in-group order: every lane resolves the whole group on registers from the 32 diagonal words (independent
+                // shuffles) and the dead mask -- no vote per survivor on the dependent chain
+                const unsigned int live = ~__ballot_sync(0xffffffffu, dead);
                 unsigned int kg = 0;
-                int cnt = 0;
-                const int nt = min(32, ns - G * 32);
-                for (int t = 0; t < nt; ++t) {
-                    const bool alive_t = lane == t && !dead && (diag & kg) == 0u && kept + cnt < p.max_det;
-                    if (__ballot_sync(0xffffffffu, alive_t)) { kg |= 1u << t; ++cnt; }
+                int room = p.max_det - kept;
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    const unsigned int dt = __shfl_sync(0xffffffffu, diag, t);
+                    const bool keep_t = ((live >> t) & 1u) && (dt & kg) == 0u && room > 0;
+                    if (keep_t) { kg |= 1u << t; --room; }
                 }
+                const int cnt = __popc(kg);
                 if ((kg >> lane) & 1u) {  // the group's kept survivors append to the kept list and to the output, in order
                     const int pos = kept + __popc(kg & ((1u << lane) - 1u));
                     const int t = surv[s];
-                    kx1[pos] = cx1[t]; ky1[pos] = cy1[t]; kx2[pos] = cx2[t]; ky2[pos] = cy2[t]; kar[pos] = car[t];
+                    kx1[pos] = sx1[s]; ky1[pos] = sy1[s]; kx2[pos] = sx2[s]; ky2[pos] = sy2[s]; kar[pos] = sar[s];
 #pragma unroll
                     for (int q = 0; q < 7; ++q) out_b[pos * 7 + q] = __fadd_rn(crow[t][q], q < shift_cols ? ((q & 1) ? shift_y : shift_x) : 0.0f);
                 }
