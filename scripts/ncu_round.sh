@@ -16,4 +16,8 @@ echo "halo capture exit $?"
 $CMD > gpurun_out/${TAG}_plain4.log 2> gpurun_out/${TAG}_plain4.err && \
 ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 100 -c 6 -f -o gpurun_out/${TAG}_gemm $CMD > gpurun_out/${TAG}_ncu_gemm.log 2>&1
 echo "gemm capture exit $?"
+WCMD="python scripts/bench_window_attn.py"
+$WCMD > gpurun_out/${TAG}_plain5.log 2> gpurun_out/${TAG}_plain5.err && \
+ncu --set full --clock-control none --import-source on -k regex:window_attn_tc -s 3 -c 1 -f -o gpurun_out/${TAG}_wattn $WCMD > gpurun_out/${TAG}_ncu_wattn.log 2>&1
+echo "window attention capture exit $?"
 ls -la gpurun_out/ | grep ${TAG}
