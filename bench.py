@@ -395,7 +395,7 @@ def run_b200(args):
 
     # p50 batch-1 latency (second half of BASELINE.json's metric): one resident image through model(x) + NMS
     latency = None
-    if world == 1 and not args.no_latency:
+    if not args.no_latency:   # at N > 1 every rank probes its own GPU (replicas); the line reports the slowest rank's percentiles
         x1 = x_dev[:1].contiguous()
         o1 = torch.zeros((1, MAX_DET, 7), dtype=torch.float32, device=dev)
         c1 = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -416,8 +416,14 @@ def run_b200(args):
             torch.cuda.synchronize()
             lat.append(a.elapsed_time(b))
         lat.sort()
-        latency = {"p50_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)], "min_ms": lat[0], "samples": len(lat),
-                   "scope": f"{args.variant} {S}x{S} batch 1: model(x) + NMS, image resident, CUDA events"}
+        pcts = [lat[len(lat) // 2], lat[int(len(lat) * 0.9)], lat[0]]
+        if world > 1:
+            t = torch.tensor(pcts, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pcts = [float(v) for v in t.tolist()]
+        latency = {"p50_ms": pcts[0], "p90_ms": pcts[1], "min_ms": pcts[2], "samples": len(lat),
+                   "scope": f"{args.variant} {S}x{S} batch 1: model(x) + NMS, image resident, CUDA events"
+                            + (f"; max over the {world} ranks (one replica per GPU)" if world > 1 else "")}
 
     # BASELINE config 4 (north_star: "scales >= 7x from 1 to 8 GPUs on tiled 4K frames"): 16 synthetic 3840x2160 frames = 128 tiles of
     # 1280^2, tiles round-robin over ranks, forward + per-tile NMS with no collective, ONE all_gather of padded rows + counts,

@@ -5,9 +5,9 @@ mkdir -p gpurun_out
 TAG=${1:-r2g}
 for n in ${2:-1 2 4 8}; do
   if [ $n = 1 ]; then
-    python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline --no-variants --no-latency > gpurun_out/${TAG}_scale_n$n.json 2> gpurun_out/${TAG}_scale_n$n.err
+    python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline --no-variants > gpurun_out/${TAG}_scale_n$n.json 2> gpurun_out/${TAG}_scale_n$n.err
   else
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 10 --warmup 3 --no-cpu-baseline --no-variants --no-latency > gpurun_out/${TAG}_scale_n$n.json 2> gpurun_out/${TAG}_scale_n$n.err
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 10 --warmup 3 --no-cpu-baseline --no-variants > gpurun_out/${TAG}_scale_n$n.json 2> gpurun_out/${TAG}_scale_n$n.err
   fi
   python - $n gpurun_out/${TAG}_scale_n$n.json <<'PY'
 import json, sys
