@@ -122,6 +122,55 @@ __global__ void focus_pad_kernel(const T* __restrict__ img, int N, int H, int W,
     }
 }
 
+// uint8 images whose rows are multiples of 16 pixels (every detector input: sizes are multiples of the stride 32): a thread
+// produces EIGHT output pixels from six 16-byte loads (3 channels x 2 rows x 16 input columns) and writes 256 contiguous bytes.
+// The one-pixel-per-thread form issued six 2-byte loads per 32-byte output (26 % of the HBM peak, ncu: profiles/
+// r2l_ncu_memory_bound_kernels.md).  Same arithmetic per element (__fdiv_rn(u8, 255)): bit-identical output.
+__global__ void __launch_bounds__(256)
+focus_pad8_u8_kernel(const uint8_t* __restrict__ img, int N, int H, int W, __nv_bfloat16* __restrict__ y) {
+    const int Ho = H / 2, Wo = W / 2, Wp = Wo + 4, segs = Wo / 8;
+    const long plane = (long)H * W;
+    const long items = (long)N * Ho * segs;
+    for (long it = blockIdx.x * (long)blockDim.x + threadIdx.x; it < items; it += (long)gridDim.x * blockDim.x) {
+        const int seg = (int)(it % segs);
+        const long r = it / segs;            // padded output row (n * Ho + oy)
+        const int oy = (int)(r % Ho);
+        const long n = r / Ho;
+        const uint8_t* src = img + n * 3 * plane + (long)(2 * oy) * W + 16 * seg;
+        uint4 top[3], bot[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            top[c] = __ldg(reinterpret_cast<const uint4*>(src + c * plane));
+            bot[c] = __ldg(reinterpret_cast<const uint4*>(src + c * plane + W));
+        }
+        uint4* o = reinterpret_cast<uint4*>(y + (r * Wp + 1 + 8 * seg) * 16);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float v[12];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const unsigned int tw = (&top[c].x)[i >> 1] >> ((i & 1) * 16), bw = (&bot[c].x)[i >> 1] >> ((i & 1) * 16);
+                v[0 * 3 + c] = __fdiv_rn((float)(tw & 0xffu), 255.0f);
+                v[1 * 3 + c] = __fdiv_rn((float)(bw & 0xffu), 255.0f);
+                v[2 * 3 + c] = __fdiv_rn((float)((tw >> 8) & 0xffu), 255.0f);
+                v[3 * 3 + c] = __fdiv_rn((float)((bw >> 8) & 0xffu), 255.0f);
+            }
+            uint4 a, b;
+            a.x = pack_bf16x2(v[0], v[1]); a.y = pack_bf16x2(v[2], v[3]); a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
+            b.x = pack_bf16x2(v[8], v[9]); b.y = pack_bf16x2(v[10], v[11]); b.z = 0u; b.w = 0u;
+            o[2 * i] = a;
+            o[2 * i + 1] = b;
+        }
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        if (seg == 0) { uint4* o0 = reinterpret_cast<uint4*>(y + (r * Wp) * 16); o0[0] = z; o0[1] = z; }   // left pad column
+        if (seg == segs - 1) {                                                                                // three right pad columns
+            uint4* o1 = reinterpret_cast<uint4*>(y + (r * Wp + 1 + Wo) * 16);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) o1[q] = z;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // letterbox + BGR->RGB + HWC->CHW (augmentation.py:442-496, detect.py:131-132), OpenCV's 8-bit INTER_LINEAR
 // ---------------------------------------------------------------------------------------------
@@ -293,12 +342,25 @@ __global__ void cbam_pool_kernel(const __nv_bfloat16* __restrict__ x, long pitch
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] = 0.f; m[j] = -FLT_MAX; }
     if (pl < lanes) {
-        for (int p = p0 + pl; p < p1; p += lanes) {
-            const uint4 u = *reinterpret_cast<const uint4*>(x + ((long)n * HW + p) * pitch + g * 8);
-            float f[8];
-            unpack8(u, f);
+        // eight independent 16-byte loads in flight per thread (one load per iteration was latency-bound: 64 dependent round trips
+        // per thread, 39 us for the 105 MB map of skyeye_l's P4 level)
+        constexpr int U = 8;
+        for (int pb = p0 + pl; pb < p1; pb += lanes * U) {
+            uint4 u[U];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { s[j] += f[j]; m[j] = fmaxf(m[j], f[j]); }
+            for (int k = 0; k < U; ++k) {
+                const int p = pb + k * lanes;
+                u[k] = p < p1 ? __ldg(reinterpret_cast<const uint4*>(x + ((long)n * HW + p) * pitch + g * 8)) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                if (pb + k * lanes < p1) {
+                    float f[8];
+                    unpack8(u[k], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { s[j] += f[j]; m[j] = fmaxf(m[j], f[j]); }
+                }
+            }
         }
     }
     extern __shared__ float sh[];  // [lanes][C] sums then [lanes][C] maxima
@@ -324,7 +386,17 @@ __global__ void cbam_mlp_kernel(const float* __restrict__ psum, const float* __r
     const int n = blockIdx.x;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float a = 0.f, b = -FLT_MAX;
-        for (int s = 0; s < slabs; ++s) { a += psum[((long)n * slabs + s) * C + c]; b = fmaxf(b, pmax[((long)n * slabs + s) * C + c]); }
+        for (int s0 = 0; s0 < slabs; s0 += 8) {  // eight independent loads of each array in flight (the sum order stays s = 0, 1, ...)
+            float ps[8], pm[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const bool ok = s0 + k < slabs;
+                ps[k] = ok ? __ldg(psum + ((long)n * slabs + s0 + k) * C + c) : 0.f;
+                pm[k] = ok ? __ldg(pmax + ((long)n * slabs + s0 + k) * C + c) : -FLT_MAX;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { a += ps[k]; b = fmaxf(b, pm[k]); }
+        }
         avg[c] = a / (float)HW;
         mx[c] = b;
     }
@@ -332,14 +404,16 @@ __global__ void cbam_mlp_kernel(const float* __restrict__ psum, const float* __r
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     for (int r = warp; r < R; r += nw) {
         float a = 0.f, b = 0.f;
-        for (int c = lane; c < C; c += 32) { const float w = w0[r * C + c]; a += w * avg[c]; b += w * mx[c]; }
+#pragma unroll 8
+        for (int c = lane; c < C; c += 32) { const float w = __ldg(w0 + r * C + c); a += w * avg[c]; b += w * mx[c]; }
         a = warp_sum(a); b = warp_sum(b);
         if (lane == 0) { ha[r] = fmaxf(a, 0.f); hm[r] = fmaxf(b, 0.f); }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float a = 0.f;
-        for (int r = 0; r < R; ++r) a += w1[c * R + r] * (ha[r] + hm[r]);
+#pragma unroll 8
+        for (int r = 0; r < R; ++r) a += __ldg(w1 + c * R + r) * (ha[r] + hm[r]);
         att[(long)n * C + c] = 1.0f / (1.0f + expf(-a));
     }
 }
@@ -595,12 +669,18 @@ __device__ __forceinline__ Blk2x blk2x(int bi, int bj, int Hk, int Wk) {
     return b;
 }
 // four source vectors (8 channels at `c`) -> the four interpolated vectors of the block: o[0] = (ya, xa), o[1] = (ya, xb), o[2] = (yb, xa), o[3] = (yb, xb)
-__device__ __forceinline__ void interp2x8(const __nv_bfloat16* __restrict__ t, long pitch, long img0, int Wk, const Blk2x& b, int c, float (&o)[4][8]) {
+__device__ __forceinline__ void load2x8(const __nv_bfloat16* __restrict__ t, long pitch, long img0, int Wk, const Blk2x& b, int c, uint4 (&u)[4]) {
+    u[0] = __ldg(reinterpret_cast<const uint4*>(t + (img0 + (long)b.r0 * Wk + b.c0) * pitch + c));
+    u[1] = __ldg(reinterpret_cast<const uint4*>(t + (img0 + (long)b.r0 * Wk + b.c1) * pitch + c));
+    u[2] = __ldg(reinterpret_cast<const uint4*>(t + (img0 + (long)b.r1 * Wk + b.c0) * pitch + c));
+    u[3] = __ldg(reinterpret_cast<const uint4*>(t + (img0 + (long)b.r1 * Wk + b.c1) * pitch + c));
+}
+__device__ __forceinline__ void interp2x8(const uint4 (&u)[4], float (&o)[4][8]) {
     float s00[8], s01[8], s10[8], s11[8];
-    unpack8(*reinterpret_cast<const uint4*>(t + (img0 + (long)b.r0 * Wk + b.c0) * pitch + c), s00);
-    unpack8(*reinterpret_cast<const uint4*>(t + (img0 + (long)b.r0 * Wk + b.c1) * pitch + c), s01);
-    unpack8(*reinterpret_cast<const uint4*>(t + (img0 + (long)b.r1 * Wk + b.c0) * pitch + c), s10);
-    unpack8(*reinterpret_cast<const uint4*>(t + (img0 + (long)b.r1 * Wk + b.c1) * pitch + c), s11);
+    unpack8(u[0], s00);
+    unpack8(u[1], s01);
+    unpack8(u[2], s10);
+    unpack8(u[3], s11);
     const float2 w75 = make_float2(0.75f, 0.75f), w25 = make_float2(0.25f, 0.25f);
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
@@ -615,7 +695,7 @@ __device__ __forceinline__ void interp2x8(const __nv_bfloat16* __restrict__ t, l
     }
 }
 // one CTA per block row bi of an image: scores of output rows 2bi-1, 2bi staged in shared memory ([2][heads][W]), coalesced stores
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 cla_score2x_kernel(const __nv_bfloat16* __restrict__ q, long qpitch, const __nv_bfloat16* __restrict__ k, long kpitch,
                    int N, int H, int W, int Hk, int Wk, int Cq, int heads, float scale, float* __restrict__ s) {
     extern __shared__ float srow[];  // [2][heads][W]
@@ -630,18 +710,21 @@ cla_score2x_kernel(const __nv_bfloat16* __restrict__ q, long qpitch, const __nv_
             const int c = cbase + lane * 8;
             float part[4] = {0.f, 0.f, 0.f, 0.f};
             if (c < Cq) {
-                float kv[4][8];
-                interp2x8(k, kpitch, kimg, Wk, b, c, kv);
                 const int ys[4] = {b.ya, b.ya, b.yb, b.yb}, xs[4] = {b.xa, b.xb, b.xa, b.xb};
                 const bool ok[4] = {va && ua, va && ub, vb && ua, vb && ub};
+                uint4 ku[4], qu[4];   // all eight loads of the block are in flight before the first is used
+                load2x8(k, kpitch, kimg, Wk, b, c, ku);
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    qu[t] = ok[t] ? __ldg(reinterpret_cast<const uint4*>(q + (qimg + (long)ys[t] * W + xs[t]) * qpitch + c)) : make_uint4(0u, 0u, 0u, 0u);
+                float kv[4][8];
+                interp2x8(ku, kv);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    if (ok[t]) {
-                        float qv[8];
-                        unpack8(*reinterpret_cast<const uint4*>(q + (qimg + (long)ys[t] * W + xs[t]) * qpitch + c), qv);
+                    float qv[8];
+                    unpack8(qu[t], qv);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) part[t] += qv[j] * kv[t][j];
-                    }
+                    for (int j = 0; j < 8; ++j) part[t] += qv[j] * kv[t][j];   // (zeros where the output pixel does not exist)
                 }
             }
             for (int o = lph >> 1; o > 0; o >>= 1) {
@@ -689,7 +772,9 @@ cla_apply2x_kernel(const float* __restrict__ s, const float* __restrict__ st, co
         const bool va = b.ya >= 0, vb = b.yb < H, ua = b.xa >= 0, ub = b.xb < W;
         for (int c = lane * 8; c < Cv; c += 256) {
             float ov[4][8];
-            interp2x8(v, vpitch, vimg, Wk, b, c, ov);
+            uint4 vu[4];
+            load2x8(v, vpitch, vimg, Wk, b, c, vu);
+            interp2x8(vu, ov);
             const int g = c / cph;
             const int ys[4] = {b.ya, b.ya, b.yb, b.yb}, xs[4] = {b.xa, b.xb, b.xa, b.xb};
             const bool ok[4] = {va && ua, va && ub, vb && ua, vb && ub};
@@ -814,8 +899,14 @@ int launch_focus_pad(const void* img, int img_dtype, int n, int h, int w, void* 
         if (img_dtype == SKB_F32) focus_pad_kernel<float, true><<<rows, 256, 0, st>>>((const float*)img, n, h, w, y, tiles, frame_h, frame_w);
         else focus_pad_kernel<uint8_t, true><<<rows, 256, 0, st>>>((const uint8_t*)img, n, h, w, y, tiles, frame_h, frame_w);
     } else {
-        if (img_dtype == SKB_F32) focus_pad_kernel<float, false><<<rows, 256, 0, st>>>((const float*)img, n, h, w, y, nullptr, 0, 0);
-        else focus_pad_kernel<uint8_t, false><<<rows, 256, 0, st>>>((const uint8_t*)img, n, h, w, y, nullptr, 0, 0);
+        if (img_dtype == SKB_F32) {
+            focus_pad_kernel<float, false><<<rows, 256, 0, st>>>((const float*)img, n, h, w, y, nullptr, 0, 0);
+        } else if (w % 32 == 0 && ((uintptr_t)img & 15) == 0) {   // 16-byte loads: rows of a multiple of 16 bytes, 8 output pixels per thread
+            const long items = (long)rows * (w / 16);
+            focus_pad8_u8_kernel<<<grid_for(items, 256), 256, 0, st>>>((const uint8_t*)img, n, h, w, y);
+        } else {
+            focus_pad_kernel<uint8_t, false><<<rows, 256, 0, st>>>((const uint8_t*)img, n, h, w, y, nullptr, 0, 0);
+        }
     }
     SKB_LAUNCH_CHECK();
     return SKB_OK;
@@ -898,7 +989,7 @@ extern "C" int skb_cbam_bf16(const skb_view* x, const float* w0, const float* w1
     const int lanes = 256 / C8;
     cbam_pool_kernel<<<dim3(slabs, N), 256, sizeof(float) * 2 * lanes * C, st>>>((const __nv_bfloat16*)x->ptr, x->pitch, HW, C, slabs, psum, pmax);
     SKB_LAUNCH_CHECK();
-    cbam_mlp_kernel<<<N, 256, sizeof(float) * (2 * C + 2 * reduced), st>>>(psum, pmax, slabs, HW, C, reduced, w0, w1, att);
+    cbam_mlp_kernel<<<N, 1024, sizeof(float) * (2 * C + 2 * reduced), st>>>(psum, pmax, slabs, HW, C, reduced, w0, w1, att);  // latency-bound: one row / channel per thread
     SKB_LAUNCH_CHECK();
     const long npix = (long)N * HW;
     cbam_stats_kernel<<<grid_for(npix, 8), 256, 0, st>>>((const __nv_bfloat16*)x->ptr, x->pitch, att, npix, HW, C, stats);
