@@ -72,12 +72,11 @@ decode_kernel(const DecodeParams p, float* __restrict__ det) {
         float* dst = det + ((long)b * p.rows_per_image + L.row0 + (long)a * hw + pix0) * p.no;
         float* rdst = L.raw_out ? L.raw_out + (((long)b * p.na + a) * hw + pix0) * p.no : nullptr;
         const float aw = L.anchor[a][0], ah = L.anchor[a][1];
-        for (int i = threadIdx.x; i < per_a; i += DEC_THREADS) {
+        // one output element: raw logit r and decoded value v of flat index i = pixel * no + output
+        auto elem = [&](int i, float& r, float& v) {
             const int px = (int)(((unsigned int)i * p.no_magic) >> 20), o = i - px * p.no;
-            const float r = sin_[px * (4 * nch4) + a * p.no + o];
-            if (rdst) rdst[i] = r;
+            r = sin_[px * (4 * nch4) + a * p.no + o];
             const float s = sigmoid_acc(r);
-            float v;
             if (o < 2) {
                 // (s*2 - 0.5 + grid) * stride   (detector.py:137); grid order (x, y) (detector.py:115)
                 const float g = o == 0 ? sgx[px] : sgy[px];
@@ -89,7 +88,27 @@ decode_kernel(const DecodeParams p, float* __restrict__ det) {
             } else {
                 v = s;
             }
-            dst[i] = v;
+        };
+        // both destination runs are contiguous: 16-byte stores of four consecutive elements when the runs allow it (every
+        // detector shape: the run starts are multiples of 4 floats), scalar stores otherwise
+        const bool vec = (per_a & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (!rdst || (reinterpret_cast<uintptr_t>(rdst) & 15) == 0);
+        if (vec) {
+            for (int i4 = 4 * (int)threadIdx.x; i4 < per_a; i4 += 4 * DEC_THREADS) {
+                float4 rr, vv;
+                elem(i4, rr.x, vv.x);
+                elem(i4 + 1, rr.y, vv.y);
+                elem(i4 + 2, rr.z, vv.z);
+                elem(i4 + 3, rr.w, vv.w);
+                if (rdst) *reinterpret_cast<float4*>(rdst + i4) = rr;
+                *reinterpret_cast<float4*>(dst + i4) = vv;
+            }
+        } else {
+            for (int i = threadIdx.x; i < per_a; i += DEC_THREADS) {
+                float r, v;
+                elem(i, r, v);
+                if (rdst) rdst[i] = r;
+                dst[i] = v;
+            }
         }
     }
 }
