@@ -384,8 +384,10 @@ def run_b200(args):
                 "share_of_step": table[dom]["share"],
                 "algorithmic_flops_per_launch": d["flops"] / d["calls"], "algorithmic_bytes_per_launch": d["bytes"] / d["calls"],
                 "note": "attention at head_dim 64: the MUFU pipe (16 ex2/clk/SM measured, 256 flop per exponential) caps it at "
-                        "~1.12 PFLOP/s at 1.85 GHz; measured co-limits are the MMA-issuing thread (~100 cycles per tcgen05.mma) and "
-                        "~100-cycle mbarrier round trips (profiles/r1m_attention_pipeline.md)" if dom == "attention" else ""}
+                        "~1.12 PFLOP/s at 1.85 GHz (16 of 64 exponentials run as polynomials on the FMA pipes); the measured bound is each "
+                        "softmax warp's dependency chain through the MUFU phase (XU 70 %, tensor pipe 52 % busy), and the board sits on its "
+                        "1000 W cap (SM clock ~1.63 GHz), so cycles saved come back as clock, not as time "
+                        "(profiles/r2b_uniform_issue.md, profiles/r2k_ncu_attention.md)" if dom == "attention" else ""}
 
     # end-to-end through the public API with host buffers
     for _ in range(2):
