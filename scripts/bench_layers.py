@@ -19,6 +19,7 @@ CONV = {
     "c3x3_256_80": (16, 80, 80, 256, 256, 3, 1, True),
     "c3x3_512_40": (16, 40, 40, 512, 512, 3, 1, True),
     "c3x3_64_320": (16, 320, 320, 64, 64, 3, 1, True),
+    "c3x3_64_320_nores": (16, 320, 320, 64, 64, 3, 1, False),
     "c3x3s2_64_128": (16, 640, 640, 64, 128, 3, 2, False),
     "c3x3s2_128_256": (16, 320, 320, 128, 256, 3, 2, False),
     "c1x1_128_128_320": (16, 320, 320, 128, 128, 1, 1, False),
